@@ -1,0 +1,285 @@
+"""CPU oracle for the hot path -- TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this module.  The product package never does.
+
+It wraps ``oracle/_build/libgsl_oracle.so`` (built from ``gsl_oracle.c`` by ``oracle/Makefile``)
+and adds two slow, independent pure-Python restatements used to cross-check the C code on
+small cases.  All ``file:line`` citations are into ``/root/reference``.
+
+Parity pin: the reference ships no tests or golden vectors for this path.
+The pins are the fixtures under ``tests/golden/`` produced by ``oracle/make_golden.py``,
+which runs the reference's own functions verbatim in the build container.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from fractions import Fraction
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "libgsl_oracle.so")
+
+# Mirrors `OrcView` in gsl_oracle.c.
+VIEW_DTYPE = np.dtype(
+    [
+        ("R", np.float64, (9,)),
+        ("t", np.float64, (3,)),
+        ("fx", np.float64),
+        ("fy", np.float64),
+        ("half_w", np.float64),
+        ("half_h", np.float64),
+        ("width", np.float64),
+        ("height", np.float64),
+        ("scale_x", np.float64),
+        ("scale_y", np.float64),
+        ("seg_w", np.int32),
+        ("seg_h", np.int32),
+        ("map_offset", np.int64),
+    ],
+    align=True,
+)
+assert VIEW_DTYPE.itemsize == 176
+
+
+def build(force: bool = False) -> str:
+    """Compile the C oracle if it is missing (or `force`)."""
+    if force or not os.path.exists(_LIB_PATH):
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        L = ctypes.CDLL(_LIB_PATH)
+        i64, i32, vp, dbl = ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_double
+        L.orc_version.restype = i32
+        L.orc_max_threads.restype = i32
+        L.orc_translation.argtypes = [vp, vp, vp]
+        L.orc_translation.restype = None
+        L.orc_project.argtypes = [vp, vp, vp, vp]
+        L.orc_project.restype = i32
+        L.orc_lift_votes.argtypes = [vp, i64, vp, i32, vp, i32, i32, vp, vp, dbl, vp]
+        L.orc_lift_votes.restype = i32
+        L.orc_sqdist.argtypes = [vp, vp, i32]
+        L.orc_sqdist.restype = dbl
+        L.orc_kmeans_assign.argtypes = [vp, i64, i32, vp, i32, vp, vp]
+        L.orc_kmeans_assign.restype = None
+        L.orc_kmeans_update.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp]
+        L.orc_kmeans_update.restype = None
+        L.orc_kmeans_update_f64.argtypes = [vp, vp, i64, i32, i32, vp, vp]
+        L.orc_kmeans_update_f64.restype = None
+        _lib = L
+    return _lib
+
+
+def max_threads() -> int:
+    return int(lib().orc_max_threads())
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+# --------------------------------------------------------------------------------------
+# lifting
+# --------------------------------------------------------------------------------------
+def translation(R, p) -> np.ndarray:
+    """t = -R @ p with the probed dgemv rounding (deep_learning_segmentation.py:66)."""
+    R = np.ascontiguousarray(R, np.float64).reshape(9)
+    p = np.ascontiguousarray(p, np.float64).reshape(3)
+    t = np.empty(3, np.float64)
+    lib().orc_translation(_ptr(R), _ptr(p), _ptr(t))
+    return t
+
+
+def make_views(cameras, map_shapes, image_sizes=None) -> np.ndarray:
+    """Build the oracle's view table from reference camera dicts.
+
+    cameras      list of dicts with the cameras.json fields (deep_learning_segmentation.py:54-63)
+    map_shapes   per view (seg_h, seg_w)                          (:267)
+    image_sizes  per view (orig_w, orig_h) of the opened image    (:263); default = map size
+    Maps are assumed concatenated in view order (map_offset = running sum of seg_h*seg_w).
+    """
+    V = len(cameras)
+    views = np.zeros(V, VIEW_DTYPE)
+    off = 0
+    for v, cam in enumerate(cameras):
+        R = np.array(cam["rotation"], np.float64)
+        p = np.array(cam["position"], np.float64)
+        seg_h, seg_w = (int(s) for s in map_shapes[v])
+        ow, oh = (seg_w, seg_h) if image_sizes is None else (int(s) for s in image_sizes[v])
+        views[v]["R"] = R.reshape(9)
+        views[v]["t"] = translation(R, p)
+        views[v]["fx"] = cam["fx"]
+        views[v]["fy"] = cam["fy"]
+        views[v]["half_w"] = cam["width"] / 2
+        views[v]["half_h"] = cam["height"] / 2
+        views[v]["width"] = cam["width"]
+        views[v]["height"] = cam["height"]
+        views[v]["scale_x"] = seg_w / ow
+        views[v]["scale_y"] = seg_h / oh
+        views[v]["seg_w"] = seg_w
+        views[v]["seg_h"] = seg_h
+        views[v]["map_offset"] = off
+        off += seg_h * seg_w
+    return views
+
+
+def lift_votes(pos, views, maps, label_min=-1, n_classes=255, eps=0.0, want_near=False):
+    """assign_labels (deep_learning_segmentation.py:241-308) given the segmentation maps.
+
+    Returns (labels int32[N], near uint8[N] or None, visible_pairs int).
+    """
+    pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 3)
+    maps = np.ascontiguousarray(maps, np.int32).reshape(-1)
+    views = np.ascontiguousarray(views)
+    assert views.dtype == VIEW_DTYPE
+    N = pos.shape[0]
+    labels = np.empty(N, np.int32)
+    near = np.zeros(N, np.uint8) if want_near else None
+    vis = np.zeros(1, np.int64)
+    rc = lib().orc_lift_votes(
+        _ptr(pos), N, _ptr(views), len(views), _ptr(maps), int(label_min), int(n_classes),
+        _ptr(labels), _ptr(near) if want_near else None, float(eps), _ptr(vis),
+    )
+    if rc != 0:
+        raise ValueError("label map value outside [label_min, label_min + n_classes)")
+    return labels, near, int(vis[0])
+
+
+def _fma(a, b, c) -> float:
+    a, b, c = float(a), float(b), float(c)
+    if not (np.isfinite(a) and np.isfinite(b) and np.isfinite(c)):
+        with np.errstate(all="ignore"):
+            return float(np.float64(a) * np.float64(b) + np.float64(c))  # nan/inf: rounding is moot
+    return float(Fraction(a) * Fraction(b) + Fraction(c))
+
+
+def project_py(position, camera):
+    """Pure-Python project_gaussian (deep_learning_segmentation.py:43-82), dgemv rounding
+    made explicit with an exact-rational fma.  Independent of the C file."""
+    fx, fy = float(camera["fx"]), float(camera["fy"])
+    width, height = camera["width"], camera["height"]
+    R = [[float(v) for v in row] for row in camera["rotation"]]
+    p = [float(v) for v in camera["position"]]
+    x0, y0, z0 = (float(np.float32(v)) for v in position)
+
+    def dot(row, a, b, c):
+        return _fma(row[2], c, _fma(row[0], a, row[1] * b))
+
+    t = [dot([-e for e in row], *p) for row in R]
+    cam = [dot(R[r], x0, y0, z0) + t[r] for r in range(3)]
+    if cam[2] <= 0:
+        return None
+    x = (fx * cam[0] / cam[2]) + width / 2
+    y = (fy * cam[1] / cam[2]) + height / 2
+    if 0 <= x < width and 0 <= y < height:
+        return (int(x), int(y))
+    return None
+
+
+def lift_votes_py(pos, cameras, seg_maps, image_sizes=None):
+    """Pure-Python assign_labels (deep_learning_segmentation.py:251-306), dict-of-dicts and
+    all, for tiny cases.  `seg_maps` is a list of 2-D int arrays, one per camera."""
+    votes = {}
+    for v, cam in enumerate(cameras):
+        seg = seg_maps[v]
+        seg_h, seg_w = seg.shape
+        ow, oh = (seg_w, seg_h) if image_sizes is None else image_sizes[v]
+        hs, ws = seg_h / oh, seg_w / ow
+        for i in range(len(pos)):
+            pr = project_py(pos[i], cam)
+            if pr is None:
+                continue
+            xs = min(max(0, int(pr[0] * ws)), seg_w - 1)
+            ys = min(max(0, int(pr[1] * hs)), seg_h - 1)
+            lab = int(seg[ys, xs])
+            d = votes.setdefault(i, {})
+            d[lab] = d.get(lab, 0) + 1
+    out = np.full(len(pos), -1, np.int32)
+    for i, d in votes.items():
+        out[i] = max(d.items(), key=lambda kv: kv[1])[0]
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# K-means
+# --------------------------------------------------------------------------------------
+def kmeans_assign(data, centroids, want_gap=False):
+    """Nearest centroid, scipy-order float64 distance (k_means.py:116-122)."""
+    data = np.ascontiguousarray(data, np.float32)
+    centroids = np.ascontiguousarray(centroids, np.float32)
+    N, D = data.shape
+    K = centroids.shape[0]
+    labels = np.empty(N, np.int64)
+    gap = np.empty(N, np.float64) if want_gap else None
+    lib().orc_kmeans_assign(_ptr(data), N, D, _ptr(centroids), K, _ptr(labels),
+                            _ptr(gap) if want_gap else None)
+    return (labels, gap) if want_gap else labels
+
+
+def kmeans_update(data, labels, centroids):
+    """New centroids, float32 sequential mean (k_means.py:125-128).  Returns (f32[K,D], counts)."""
+    data = np.ascontiguousarray(data, np.float32)
+    labels = np.ascontiguousarray(labels, np.int64)
+    centroids = np.ascontiguousarray(centroids, np.float32)
+    N, D = data.shape
+    K = centroids.shape[0]
+    new = np.empty((K, D), np.float32)
+    counts = np.empty(K, np.int64)
+    lib().orc_kmeans_update(_ptr(data), _ptr(labels), N, D, K, _ptr(centroids), _ptr(new), _ptr(counts))
+    return new, counts
+
+
+def kmeans_update_f64(data, labels, centroids):
+    """Exact-mean yardstick (float64 accumulation); not reference arithmetic."""
+    data = np.ascontiguousarray(data, np.float32)
+    labels = np.ascontiguousarray(labels, np.int64)
+    centroids = np.ascontiguousarray(centroids, np.float32)
+    N, D = data.shape
+    K = centroids.shape[0]
+    new = np.empty((K, D), np.float64)
+    lib().orc_kmeans_update_f64(_ptr(data), _ptr(labels), N, D, K, _ptr(centroids), _ptr(new))
+    return new
+
+
+def sqdist(u, v) -> float:
+    u = np.ascontiguousarray(u, np.float32)
+    v = np.ascontiguousarray(v, np.float32)
+    return float(lib().orc_sqdist(_ptr(u), _ptr(v), u.shape[0]))
+
+
+def kmeans_run(data, k, max_iter=100, tol=1e-4, init_idx=None, trace=None):
+    """Lloyd loop of k_means_kd_tree / k_means_with_color (k_means.py:46-96 / 107-144)
+    on the concatenated feature block, without the prints and the recolouring.
+
+    init: `np.random.choice(N, k, replace=False)` from the global stream (:63/:111) unless
+    `init_idx` is given.  Returns (centroids f32[K,D], labels int64[N], iterations_run).
+    `trace`, if a list, receives (centroids_used, labels, new_centroids, shift) per iteration.
+    """
+    data = np.ascontiguousarray(data, np.float32)
+    N = data.shape[0]
+    if init_idx is None:
+        init_idx = np.random.choice(N, k, replace=False)
+    centroids = data[init_idx]
+    it = 0
+    for it in range(max_iter):
+        labels = kmeans_assign(data, centroids)
+        new, _ = kmeans_update(data, labels, centroids)
+        shift = np.linalg.norm(new - centroids)            # :83/:131
+        if trace is not None:
+            trace.append((centroids.copy(), labels.copy(), new.copy(), float(shift)))
+        if shift < tol:                                    # :84-86 break BEFORE the swap
+            break
+        centroids = new                                    # :88/:136
+    labels = kmeans_assign(data, centroids)                # :92-96/:140-144
+    return centroids, labels, it + 1
