@@ -1,0 +1,294 @@
+// K-means labelling for sm_100a: assignment, fused per-cluster sums, finalize.
+//
+// Replaces the per-point KDTree.query loop and the K boolean-mask means of
+// k_means_with_color / k_means_kd_tree (3D_clustering/k_means.py:113-144, "km" below).
+//
+//   kmeans_step_kernel<kAccumulate>
+//        persistent CTAs, one tile of TR rows at a time staged in shared memory
+//        (coalesced float4 loads of the contiguous [TR x D] block).  One thread per row
+//        evaluates scipy's float64 squared distance to every centroid in scipy's own
+//        summation order (four running lanes, no FMA; see oracle/gsl_oracle.c) and keeps
+//        the first minimum.  With kAccumulate the tile is then reduced per cluster:
+//        each warp owns the clusters k = warp (mod warps), finds their rows with ballots in
+//        ascending row order, and adds them lane-per-dimension in float64 into the CTA's
+//        [K][D+1] accumulator in shared memory -- a segmented reduction with no atomics
+//        and a fixed order, so results are bit-reproducible.
+//   kmeans_reduce_kernel      fixed-order sum of the per-CTA partials -> sums[K][D+1]
+//   kmeans_finalize_kernel    new = float32(sum / count) or old; shift = ||new - old||_F
+//
+// Compiled with -fmad=false (the distance must not be contracted).
+#include "common.cuh"
+
+namespace gsl {
+
+constexpr int kStepThreads = 256;   // rows per tile == threads per CTA
+constexpr int kStepWarps = kStepThreads / 32;
+
+struct StepSmem {
+    // byte offsets into dynamic shared memory
+    size_t tile, cent, acc, lab, total;
+    int pitch;   // row pitch of the tile in floats (odd -> conflict-free row-per-lane reads)
+};
+
+static inline StepSmem step_layout(int D, int K, bool accumulate)
+{
+    StepSmem s;
+    s.pitch = D | 1;
+    size_t o = 0;
+    s.acc = o;  o += accumulate ? align_up((size_t)K * (D + 1) * sizeof(double), 16) : 0;
+    s.tile = o; o += align_up((size_t)kStepThreads * s.pitch * sizeof(float), 16);
+    s.cent = o; o += align_up((size_t)K * D * sizeof(float), 16);
+    s.lab = o;  o += (size_t)kStepThreads * sizeof(int);
+    s.total = o;
+    return s;
+}
+
+// scipy ckdtree sqeuclidean_distance_double on float64 copies of float32 values.
+__device__ __forceinline__ double sqdist_scipy(const float *__restrict__ c, const float *__restrict__ x, int D)
+{
+    double a0 = 0., a1 = 0., a2 = 0., a3 = 0.;
+    int i = 0;
+    for (; i + 4 <= D; i += 4) {
+        const double d0 = (double)c[i] - (double)x[i];
+        const double d1 = (double)c[i + 1] - (double)x[i + 1];
+        const double d2 = (double)c[i + 2] - (double)x[i + 2];
+        const double d3 = (double)c[i + 3] - (double)x[i + 3];
+        a0 += d0 * d0; a1 += d1 * d1; a2 += d2 * d2; a3 += d3 * d3;
+    }
+    double s = a0 + a1 + a2 + a3;
+    for (; i < D; ++i) {
+        const double d = (double)c[i] - (double)x[i];
+        s += d * d;
+    }
+    return s;
+}
+
+template <bool kAccumulate>
+__global__ void __launch_bounds__(kStepThreads)
+kmeans_step_kernel(const float *__restrict__ data, int64_t N, int D, const float *__restrict__ centroids,
+                   int K, int32_t *__restrict__ labels, double *__restrict__ partials,
+                   StepSmem L, int vec_ok)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    double *acc = reinterpret_cast<double *>(smem + L.acc);
+    float *tile = reinterpret_cast<float *>(smem + L.tile);
+    float *cent = reinterpret_cast<float *>(smem + L.cent);
+    int *lab = reinterpret_cast<int *>(smem + L.lab);
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int pitch = L.pitch;
+
+    for (int i = t; i < K * D; i += kStepThreads) cent[i] = centroids[i];
+    if (kAccumulate)
+        for (int i = t; i < K * (D + 1); i += kStepThreads) acc[i] = 0.0;
+
+    const int64_t n_tiles = (N + kStepThreads - 1) / kStepThreads;
+    for (int64_t tl = blockIdx.x; tl < n_tiles; tl += gridDim.x) {
+        const int64_t row0 = tl * kStepThreads;
+        const int rows = (int)min((int64_t)kStepThreads, N - row0);
+        __syncthreads();   // previous tile fully consumed (and cent/acc initialised)
+        // ---- stage the contiguous [rows x D] block, repitched to `pitch` floats per row
+        const float *src = data + row0 * D;
+        const int n_el = rows * D;
+        if (vec_ok && rows == kStepThreads) {
+            const float4 *src4 = reinterpret_cast<const float4 *>(src);
+            for (int i = t; i < (n_el >> 2); i += kStepThreads) {
+                const float4 v = __ldcs(src4 + i);
+                const int e = i << 2;
+                int r = e / D, d = e - r * D;
+                const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    tile[r * pitch + d] = vv[j];
+                    if (++d == D) { d = 0; ++r; }
+                }
+            }
+        } else {
+            for (int i = t; i < n_el; i += kStepThreads) {
+                const int r = i / D, d = i - r * D;
+                tile[r * pitch + d] = __ldcs(src + i);
+            }
+        }
+        __syncthreads();
+        // ---- assignment: thread = row
+        int mine = -1;
+        if (t < rows) {
+            const float *x = tile + t * pitch;
+            double best = sqdist_scipy(cent, x, D);
+            mine = 0;
+            for (int k = 1; k < K; ++k) {
+                const double d2 = sqdist_scipy(cent + k * D, x, D);
+                if (d2 < best) { best = d2; mine = k; }
+            }
+            labels[row0 + t] = mine;
+        }
+        if (!kAccumulate) continue;
+        lab[t] = mine;
+        __syncthreads();
+        // ---- segmented reduction: warp owns clusters k = warp, warp + W, ...
+        for (int k = warp; k < K; k += kStepWarps) {
+            int cnt = 0;
+            for (int d0 = 0; d0 < D; d0 += 32) {
+                const int d = d0 + lane;
+                double s = 0.0;
+                cnt = 0;
+                for (int r0 = 0; r0 < kStepThreads; r0 += 32) {
+                    unsigned m = __ballot_sync(0xffffffffu, lab[r0 + lane] == k);
+                    cnt += __popc(m);
+                    while (m) {
+                        const int r = r0 + __ffs(m) - 1;
+                        m &= m - 1;
+                        if (d < D) s += (double)tile[r * pitch + d];
+                    }
+                }
+                if (d < D && cnt) acc[k * (D + 1) + d] += s;
+            }
+            if (lane == 0 && cnt) acc[k * (D + 1) + D] += (double)cnt;
+        }
+    }
+    if (kAccumulate) {
+        __syncthreads();
+        double *out = partials + (size_t)blockIdx.x * K * (D + 1);
+        for (int i = t; i < K * (D + 1); i += kStepThreads) out[i] = acc[i];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+kmeans_reduce_kernel(const double *__restrict__ partials, int n_parts, int n_el, double *__restrict__ sums)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_el) return;
+    double s = 0.0;
+    for (int p = 0; p < n_parts; ++p) s += partials[(size_t)p * n_el + i];
+    sums[i] = s;
+}
+
+// One CTA.  new = (float)(sum / count) (float64 quotient, as np.mean's true_divide with an
+// intp count does, km:126) or old when empty; shift = Frobenius norm of the float32 difference.
+__global__ void __launch_bounds__(256)
+kmeans_finalize_kernel(const double *__restrict__ sums, const float *__restrict__ old_c, int K, int D,
+                       float *__restrict__ new_c, float *__restrict__ shift)
+{
+    __shared__ double red[8];
+    double sq = 0.0;
+    for (int i = threadIdx.x; i < K * D; i += blockDim.x) {
+        const int k = i / D, d = i - k * D;
+        const double n = sums[k * (D + 1) + D];
+        const float o = old_c[i];
+        const float v = n > 0.0 ? (float)(sums[k * (D + 1) + d] / n) : o;
+        new_c[i] = v;
+        const float df = v - o;
+        sq += (double)df * (double)df;
+    }
+    for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < 8; ++w) s += red[w];
+        *shift = (float)sqrt(s);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+recolor_kernel(const int32_t *__restrict__ labels, int64_t N, const float *__restrict__ palette,
+               float *__restrict__ colors)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int c = labels[i] & 7;    // labels >= 0, so & 7 == % len(COLORS) (km:100, :148)
+    colors[3 * i + 0] = palette[3 * c + 0];
+    colors[3 * i + 1] = palette[3 * c + 1];
+    colors[3 * i + 2] = palette[3 * c + 2];
+}
+
+static int step_grid(int64_t N)
+{
+    const int64_t tiles = (N + kStepThreads - 1) / kStepThreads;
+    const int64_t cap = (int64_t)sm_count() * 2;
+    return (int)(tiles < cap ? (tiles < 1 ? 1 : tiles) : cap);
+}
+
+}  // namespace gsl
+
+using namespace gsl;
+
+static int check_kd(const char *who, int64_t N, int D, int K)
+{
+    if (N < 0) return fail(GSL_EINVAL, "%s: negative N", who);
+    if (D < 1 || D > GSL_KMEANS_MAX_D) return fail(GSL_EINVAL, "%s: D=%d not in [1, %d]", who, D, GSL_KMEANS_MAX_D);
+    if (K < 1 || K > GSL_KMEANS_MAX_K) return fail(GSL_EINVAL, "%s: K=%d not in [1, %d]", who, K, GSL_KMEANS_MAX_K);
+    return GSL_OK;
+}
+
+extern "C" size_t gsl_kmeans_workspace_bytes(int64_t N, int D, int K)
+{
+    if (N < 0 || D < 1 || K < 1) return 0;
+    const size_t parts = (size_t)sm_count() * 2;
+    const size_t step = parts * (size_t)K * (D + 1) * sizeof(double) + 256;
+    const size_t ord = ordered_workspace_bytes(N, K);
+    return step > ord ? step : ord;
+}
+
+template <bool kAcc>
+static int launch_step(const float *data, int64_t N, int D, const float *centroids, int K,
+                       int32_t *labels, double *partials, int grid, cudaStream_t st)
+{
+    const StepSmem L = step_layout(D, K, kAcc);
+    if (L.total > 227 * 1024) return fail(GSL_EINVAL, "kmeans: K=%d, D=%d needs %zu B of shared memory (> 227 KB)", K, D, L.total);
+    GSL_CUDA_TRY(cudaFuncSetAttribute(kmeans_step_kernel<kAcc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    const int vec_ok = (((uintptr_t)data & 15) == 0) && (((size_t)kStepThreads * D) % 4 == 0);
+    kmeans_step_kernel<kAcc><<<grid, kStepThreads, L.total, st>>>(data, N, D, centroids, K, labels, partials, L, vec_ok);
+    GSL_LAUNCH_CHECK("kmeans_step_kernel");
+    return GSL_OK;
+}
+
+extern "C" int gsl_kmeans_assign(const float *data, int64_t N, int D, const float *centroids, int K,
+                                 int32_t *labels, void *ws, size_t ws_bytes, void *stream)
+{
+    (void)ws; (void)ws_bytes;
+    if (int rc = check_kd("gsl_kmeans_assign", N, D, K)) return rc;
+    if (N == 0) return GSL_OK;
+    if (!data || !centroids || !labels) return fail(GSL_EINVAL, "gsl_kmeans_assign: null pointer");
+    return launch_step<false>(data, N, D, centroids, K, labels, nullptr, step_grid(N), (cudaStream_t)stream);
+}
+
+extern "C" int gsl_kmeans_step(const float *data, int64_t N, int D, const float *centroids, int K,
+                               int32_t *labels, double *sums, void *ws, size_t ws_bytes, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = check_kd("gsl_kmeans_step", N, D, K)) return rc;
+    if (!centroids || !sums) return fail(GSL_EINVAL, "gsl_kmeans_step: null pointer");
+    const int n_el = K * (D + 1);
+    if (N == 0) {
+        GSL_CUDA_TRY(cudaMemsetAsync(sums, 0, sizeof(double) * (size_t)n_el, st));
+        return GSL_OK;
+    }
+    if (!data || !labels || !ws) return fail(GSL_EINVAL, "gsl_kmeans_step: null pointer");
+    if (ws_bytes < gsl_kmeans_workspace_bytes(N, D, K)) return fail(GSL_EWORKSPACE, "gsl_kmeans_step: workspace %zu < %zu", ws_bytes, gsl_kmeans_workspace_bytes(N, D, K));
+    double *partials = reinterpret_cast<double *>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+    const int grid = step_grid(N);
+    if (int rc = launch_step<true>(data, N, D, centroids, K, labels, partials, grid, st)) return rc;
+    kmeans_reduce_kernel<<<(n_el + 255) / 256, 256, 0, st>>>(partials, grid, n_el, sums);
+    GSL_LAUNCH_CHECK("kmeans_reduce_kernel");
+    return GSL_OK;
+}
+
+extern "C" int gsl_kmeans_finalize(const double *sums, const float *old_centroids, int K, int D,
+                                   float *new_centroids, float *shift, void *stream)
+{
+    if (int rc = check_kd("gsl_kmeans_finalize", 0, D, K)) return rc;
+    if (!sums || !old_centroids || !new_centroids || !shift) return fail(GSL_EINVAL, "gsl_kmeans_finalize: null pointer");
+    kmeans_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(sums, old_centroids, K, D, new_centroids, shift);
+    GSL_LAUNCH_CHECK("kmeans_finalize_kernel");
+    return GSL_OK;
+}
+
+extern "C" int gsl_recolor(const int32_t *labels, int64_t N, const float *palette, float *colors, void *stream)
+{
+    if (N < 0) return fail(GSL_EINVAL, "gsl_recolor: negative N");
+    if (N == 0) return GSL_OK;
+    if (!labels || !colors || !palette) return fail(GSL_EINVAL, "gsl_recolor: null pointer");
+    recolor_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(labels, N, palette, colors);
+    GSL_LAUNCH_CHECK("recolor_kernel");
+    return GSL_OK;
+}

@@ -1,0 +1,256 @@
+// Reference-order centroid update for sm_100a.
+//
+// NumPy evaluates `data[labels == c].mean(axis=0)` (3D_clustering/k_means.py:125-128) as a
+// float32 SEQUENTIAL sum over the members in index order, then one float64 division rounded
+// to float32 (see oracle/gsl_oracle.c: orc_kmeans_update).  Float32 addition is not
+// associative, so reproducing the reference bit for bit means keeping that order: one serial
+// chain per (cluster, dimension).  The K*D chains are independent, so the work is:
+//
+//   ordered_count_kernel     per 1024-row tile, member count per cluster
+//   ordered_scan_kernel      per cluster, exclusive scan of the tile counts (+ totals)
+//   ordered_start_kernel     exclusive scan of the totals -> segment starts
+//   ordered_scatter_kernel   stable scatter of row indices into per-cluster member lists
+//                            (warp match_any ranks keep ascending row order)
+//   ordered_chain_kernel     CTA per (cluster, 32 dims): all warps prefetch the next 256
+//                            member rows while warp 0 adds the current 256 in order,
+//                            lane = dimension
+//   shift_kernel             ||new - old||_F
+//
+// This is the parity mode (single device).  The throughput mode is gsl_kmeans_step's float64
+// segmented reduction, which is sharded and all-reduced.
+#include "common.cuh"
+
+namespace gsl {
+
+constexpr int kOrdTile = 1024;
+constexpr int kOrdThreads = 256;
+constexpr int kChainBatch = 256;   // members per prefetch batch (32 per warp)
+
+__global__ void __launch_bounds__(kOrdThreads)
+ordered_count_kernel(const int32_t *__restrict__ labels, int64_t N, int K, int32_t *__restrict__ tile_counts)
+{
+    extern __shared__ int hist[];
+    for (int i = threadIdx.x; i < K; i += kOrdThreads) hist[i] = 0;
+    __syncthreads();
+    const int64_t row0 = (int64_t)blockIdx.x * kOrdTile;
+    for (int r = threadIdx.x; r < kOrdTile; r += kOrdThreads) {
+        const int64_t row = row0 + r;
+        if (row < N) atomicAdd(&hist[labels[row]], 1);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < K; i += kOrdThreads) tile_counts[(size_t)blockIdx.x * K + i] = hist[i];
+}
+
+// Block k: tile_counts[:, k] -> exclusive offsets in place, total[k].
+__global__ void __launch_bounds__(kOrdThreads)
+ordered_scan_kernel(int32_t *__restrict__ tile_counts, int n_tiles, int K, int64_t *__restrict__ total)
+{
+    __shared__ int64_t part[kOrdThreads];
+    const int k = blockIdx.x, t = threadIdx.x;
+    const int seg = (n_tiles + kOrdThreads - 1) / kOrdThreads;
+    const int lo = min(t * seg, n_tiles), hi = min(lo + seg, n_tiles);
+    int64_t s = 0;
+    for (int i = lo; i < hi; ++i) s += tile_counts[(size_t)i * K + k];
+    part[t] = s;
+    __syncthreads();
+    if (t == 0) {
+        int64_t run = 0;
+        for (int i = 0; i < kOrdThreads; ++i) { const int64_t v = part[i]; part[i] = run; run += v; }
+        total[k] = run;
+    }
+    __syncthreads();
+    int64_t run = part[t];
+    for (int i = lo; i < hi; ++i) {
+        const int c = tile_counts[(size_t)i * K + k];
+        tile_counts[(size_t)i * K + k] = (int32_t)run;   // within-cluster offset (< N < 2^31)
+        run += c;
+    }
+}
+
+__global__ void ordered_start_kernel(const int64_t *__restrict__ total, int K, int64_t *__restrict__ start)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int64_t run = 0;
+        for (int k = 0; k < K; ++k) { start[k] = run; run += total[k]; }
+    }
+}
+
+__global__ void __launch_bounds__(kOrdThreads)
+ordered_scatter_kernel(const int32_t *__restrict__ labels, int64_t N, int K,
+                       const int32_t *__restrict__ tile_offsets, const int64_t *__restrict__ start,
+                       int32_t *__restrict__ members)
+{
+    extern __shared__ int wc[];                 // [8][K] counts, then absolute bases (as int64 would
+    int64_t *base = reinterpret_cast<int64_t *>(wc + 8 * K + ((8 * K) & 1));  // overflow int): [8][K] int64
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    for (int i = t; i < 8 * K; i += kOrdThreads) wc[i] = 0;
+    __syncthreads();
+    const int64_t row0 = (int64_t)blockIdx.x * kOrdTile + w * 128;
+    int lab[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const int64_t row = row0 + c * 32 + lane;
+        lab[c] = row < N ? labels[row] : -1;
+        if (lab[c] >= 0) atomicAdd(&wc[w * K + lab[c]], 1);
+    }
+    __syncthreads();
+    for (int k = t; k < K; k += kOrdThreads) {
+        int64_t run = start[k] + tile_offsets[(size_t)blockIdx.x * K + k];
+        for (int ww = 0; ww < 8; ++ww) { base[ww * K + k] = run; run += wc[ww * K + k]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const int key = lab[c] >= 0 ? lab[c] : -1 - lane;     // invalid rows never match
+        const unsigned m = __match_any_sync(0xffffffffu, key);
+        if (lab[c] >= 0) {
+            const int rank = __popc(m & ((1u << lane) - 1u));
+            const int64_t b = base[w * K + lab[c]];
+            members[b + rank] = (int32_t)(row0 + c * 32 + lane);
+        }
+        __syncwarp();
+        if (lab[c] >= 0 && lane == __ffs(m) - 1) base[w * K + lab[c]] += __popc(m);
+        __syncwarp();
+    }
+}
+
+// grid (K, ceil(D/32)); lane = dimension d0 + lane.
+__global__ void __launch_bounds__(kOrdThreads)
+ordered_chain_kernel(const float *__restrict__ data, int D, const int32_t *__restrict__ members,
+                     const int64_t *__restrict__ start, const int64_t *__restrict__ total,
+                     const float *__restrict__ old_c, float *__restrict__ new_c)
+{
+    extern __shared__ float buf[];              // [2][kChainBatch][32]
+    const int k = blockIdx.x, d = blockIdx.y * 32 + (threadIdx.x & 31);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t n = total[k], s0 = start[k];
+    const bool live = d < D;
+    if (n == 0) {
+        if (w == 0 && live) new_c[(size_t)k * D + d] = old_c[(size_t)k * D + d];   // km:126 else-branch
+        return;
+    }
+    float v[32];
+    auto fetch = [&](int64_t b0) {   // this warp's 32 rows of the batch starting at member b0
+        const int64_t mi = b0 + w * 32 + lane;
+        const int idx = mi < n ? members[s0 + mi] : -1;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int r = __shfl_sync(0xffffffffu, idx, j);
+            v[j] = (r >= 0 && live) ? __ldcs(data + (size_t)r * D + d) : 0.f;
+        }
+    };
+    auto stash = [&](int which) {
+        float *dst = buf + (size_t)which * kChainBatch * 32 + (size_t)(w * 32) * 32 + lane;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dst[j * 32] = v[j];
+    };
+    fetch(0);
+    stash(0);
+    __syncthreads();
+    float acc = -0.0f;              // (-0) + x == x for every x: same as starting from the first row
+    int cur = 0;
+    for (int64_t b0 = 0; b0 < n; b0 += kChainBatch) {
+        const bool more = b0 + kChainBatch < n;
+        if (more) fetch(b0 + kChainBatch);                 // loads in flight during the chain
+        if (w == 0) {
+            const int cnt = (int)min((int64_t)kChainBatch, n - b0);
+            const float *src = buf + (size_t)cur * kChainBatch * 32 + lane;
+            int i = 0;
+            for (; i + 8 <= cnt; i += 8) {
+                float x[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) x[j] = src[(i + j) * 32];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc = __fadd_rn(acc, x[j]);
+            }
+            for (; i < cnt; ++i) acc = __fadd_rn(acc, src[i * 32]);
+        }
+        if (more) stash(cur ^ 1);
+        __syncthreads();
+        cur ^= 1;
+    }
+    if (w == 0 && live) new_c[(size_t)k * D + d] = (float)((double)acc / (double)n);
+}
+
+__global__ void __launch_bounds__(256)
+shift_kernel(const float *__restrict__ a, const float *__restrict__ b, int n, float *__restrict__ shift)
+{
+    __shared__ double red[8];
+    double sq = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float df = a[i] - b[i];
+        sq += (double)df * (double)df;
+    }
+    for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < 8; ++w) s += red[w];
+        *shift = (float)sqrt(s);
+    }
+}
+
+struct OrdWs { size_t tile_counts, total, start, members, bytes; };
+
+static OrdWs ordered_layout(int64_t N, int K)
+{
+    OrdWs o;
+    const size_t n_tiles = (size_t)((N + kOrdTile - 1) / kOrdTile);
+    size_t off = 256;
+    o.tile_counts = off; off += align_up(n_tiles * K * sizeof(int32_t), 256);
+    o.total = off;       off += align_up((size_t)K * sizeof(int64_t), 256);
+    o.start = off;       off += align_up((size_t)K * sizeof(int64_t), 256);
+    o.members = off;     off += align_up((size_t)N * sizeof(int32_t), 256);
+    o.bytes = off;
+    return o;
+}
+
+size_t ordered_workspace_bytes(int64_t N, int K) { return ordered_layout(N, K).bytes; }
+
+}  // namespace gsl
+
+using namespace gsl;
+
+extern "C" int gsl_kmeans_update_ordered(const float *data, const int32_t *labels, int64_t N, int D, int K,
+                                         const float *old_centroids, float *new_centroids, float *shift,
+                                         void *ws, size_t ws_bytes, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N < 0 || N >= ((int64_t)1 << 31)) return fail(GSL_EINVAL, "gsl_kmeans_update_ordered: N out of range");
+    if (D < 1 || D > GSL_KMEANS_MAX_D || K < 1 || K > GSL_KMEANS_MAX_K) return fail(GSL_EINVAL, "gsl_kmeans_update_ordered: bad K/D");
+    if (!old_centroids || !new_centroids || !shift) return fail(GSL_EINVAL, "gsl_kmeans_update_ordered: null pointer");
+    if (N > 0 && (!data || !labels || !ws)) return fail(GSL_EINVAL, "gsl_kmeans_update_ordered: null pointer");
+    const OrdWs L = ordered_layout(N, K);
+    if (ws_bytes < L.bytes) return fail(GSL_EWORKSPACE, "gsl_kmeans_update_ordered: workspace %zu < %zu", ws_bytes, L.bytes);
+    unsigned char *base = reinterpret_cast<unsigned char *>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+    int32_t *tile_counts = reinterpret_cast<int32_t *>(base + L.tile_counts - 256);
+    int64_t *total = reinterpret_cast<int64_t *>(base + L.total - 256);
+    int64_t *start = reinterpret_cast<int64_t *>(base + L.start - 256);
+    int32_t *members = reinterpret_cast<int32_t *>(base + L.members - 256);
+    const int n_tiles = (int)((N + kOrdTile - 1) / kOrdTile);
+
+    if (N == 0) {
+        GSL_CUDA_TRY(cudaMemsetAsync(total, 0, sizeof(int64_t) * (size_t)K, st));
+        GSL_CUDA_TRY(cudaMemsetAsync(start, 0, sizeof(int64_t) * (size_t)K, st));
+    } else {
+        ordered_count_kernel<<<n_tiles, kOrdThreads, K * sizeof(int), st>>>(labels, N, K, tile_counts);
+        GSL_LAUNCH_CHECK("ordered_count_kernel");
+        ordered_scan_kernel<<<K, kOrdThreads, 0, st>>>(tile_counts, n_tiles, K, total);
+        GSL_LAUNCH_CHECK("ordered_scan_kernel");
+        ordered_start_kernel<<<1, 32, 0, st>>>(total, K, start);
+        GSL_LAUNCH_CHECK("ordered_start_kernel");
+        const size_t sc_smem = (size_t)(8 * K + ((8 * K) & 1)) * sizeof(int) + (size_t)8 * K * sizeof(int64_t);
+        GSL_CUDA_TRY(cudaFuncSetAttribute(ordered_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));
+        ordered_scatter_kernel<<<n_tiles, kOrdThreads, sc_smem, st>>>(labels, N, K, tile_counts, start, members);
+        GSL_LAUNCH_CHECK("ordered_scatter_kernel");
+    }
+    const size_t ch_smem = (size_t)2 * kChainBatch * 32 * sizeof(float);
+    GSL_CUDA_TRY(cudaFuncSetAttribute(ordered_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch_smem));
+    dim3 grid((unsigned)K, (unsigned)((D + 31) / 32));
+    ordered_chain_kernel<<<grid, kOrdThreads, ch_smem, st>>>(data, D, members, start, total, old_centroids, new_centroids);
+    GSL_LAUNCH_CHECK("ordered_chain_kernel");
+    shift_kernel<<<1, 256, 0, st>>>(new_centroids, old_centroids, K * D, shift);
+    GSL_LAUNCH_CHECK("shift_kernel");
+    return GSL_OK;
+}

@@ -1,0 +1,222 @@
+"""Drop-in for the reference's `deep_learning_segmentation.py` with the N x V vote loop moved to
+the GPU library.  Same public names, signatures, prints, CLI flags and output file:
+
+    load_cameras, load_gaussians, project_gaussian, assign_labels, save_labeled_ply, main
+
+What changed: `assign_labels` no longer walks Gaussians in Python (reference :274-306).  It
+still visits the cameras in order, still skips a camera whose `<input_dir>/<img_name>.png` is
+missing with the same warning (:257-259), still asks the 2-D segmenter for one map per view
+(:266) -- but each map is uploaded and packed as it arrives and one `lift_votes` call
+(include/gslift.h) produces the labels.
+
+The 2-D segmentation stage itself (SegFormer / Mask2Former / YOLO inference, reference
+:85-238) is upstream of this path and is not re-implemented.  `assign_labels` finds a
+segmenter in this order:
+  1. the `segmenter=` argument: callable(image_path, output_dir, model_type) -> int array [H, W]
+  2. a precomputed `<output_dir>/<img_name>_segmap.npy`, the file the reference's
+     `segment_image` writes for every view (:165)
+  3. the reference's own `initialize_model` / `segment_image`, imported from the checkout
+     named by $GSLIFT_REFERENCE_DIR
+"""
+from __future__ import annotations
+
+import argparse
+import importlib.util
+import json
+import os
+
+import numpy as np
+import torch
+from PIL import Image
+
+from . import ops, plyio
+
+GAUSSIAN_DTYPE = np.dtype([("position", np.float32, 3), ("scale", np.float32, 3), ("rotation", np.float32, 4)])
+
+
+def load_cameras(camera_file):
+    """cameras.json -> list of dicts (reference :17-22)."""
+    with open(camera_file, "r") as fh:
+        return json.load(fh)
+
+
+def load_gaussians(ply_file):
+    """PLY -> (structured array with `position` filled from x/y/z, parsed PLY) (reference :25-40).
+    `scale` and `rotation` stay zero, as in the reference."""
+    ply = plyio.read_ply(ply_file)
+    vertex = ply["vertex"]
+    gaussians = np.zeros(len(vertex), dtype=GAUSSIAN_DTYPE)
+    for axis, name in enumerate(("x", "y", "z")):
+        gaussians["position"][:, axis] = vertex[name]
+    return gaussians, ply
+
+
+def project_gaussian(position, camera):
+    """Scalar projection of one Gaussian mean (reference :43-82): (int x, int y) or None.
+    Kept for API parity; the fast path evaluates the same float64 expressions on the GPU."""
+    R = np.array(camera["rotation"])
+    cam = R @ position + (-R @ np.array(camera["position"]))
+    if cam[2] <= 0:
+        return None
+    w, h = camera["width"], camera["height"]
+    u = (camera["fx"] * cam[0] / cam[2]) + w / 2
+    v = (camera["fy"] * cam[1] / cam[2]) + h / 2
+    if 0 <= u < w and 0 <= v < h:
+        return (int(u), int(v))
+    return None
+
+
+# ----------------------------------------------------------------------------------------
+# segmenter plumbing (upstream stage, not part of the hot path)
+# ----------------------------------------------------------------------------------------
+_ref_module = None
+
+
+def _reference_module():
+    """Import the reference's deep_learning_segmentation.py by path (for its segmenter)."""
+    global _ref_module
+    if _ref_module is None:
+        root = os.environ.get("GSLIFT_REFERENCE_DIR")
+        path = os.path.join(root, "deep_learning_segmentation.py") if root else None
+        if not path or not os.path.exists(path):
+            raise RuntimeError(
+                "no segmenter: pass segmenter=..., provide <output_dir>/<img_name>_segmap.npy, or set "
+                "GSLIFT_REFERENCE_DIR to a checkout of the reference (its segment_image is used unchanged)")
+        spec = importlib.util.spec_from_file_location("_gslift_reference_dls", path)
+        _ref_module = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(_ref_module)
+    return _ref_module
+
+
+class _UpstreamSegmenter:
+    """Lazily builds the reference's model once and calls its segment_image per view."""
+
+    def __init__(self, model_type):
+        self.model_type = model_type
+        self._state = None
+
+    def __call__(self, image_path, output_dir, model_type):
+        ref = _reference_module()
+        if self._state is None:
+            device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+            processor, model = ref.initialize_model(self.model_type, device)
+            model.to(device)
+            self._state = (processor, model, device)
+        processor, model, device = self._state
+        return ref.segment_image(image_path, output_dir, processor, model, device, model_type)
+
+
+def _precomputed_map(output_dir, img_name):
+    path = os.path.join(output_dir, f"{img_name}_segmap.npy") if output_dir else None
+    return np.load(path) if path and os.path.exists(path) else None
+
+
+# ----------------------------------------------------------------------------------------
+# the hot path
+# ----------------------------------------------------------------------------------------
+def lift_labels(positions, cameras, seg_maps, image_sizes=None, device=None, want_near=False,
+                near_eps=1e-4, label_min=None, n_classes=None):
+    """Majority-vote labels for `positions` given one segmentation map per camera.
+
+    positions   float32 [N,3] array or device tensor
+    cameras     camera dicts, in voting order
+    seg_maps    list of int arrays [seg_h, seg_w] (NumPy or device tensors), one per camera
+    image_sizes per camera (orig_w, orig_h); default = the map's own size (scale 1.0)
+    Returns int32 NumPy labels (and the near-boundary mask when want_near).
+    """
+    device = torch.device(device if device is not None else "cuda")
+    pos = positions if isinstance(positions, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(positions, np.float32))
+    pos = pos.to(device=device, dtype=torch.float32).contiguous()
+    shapes = [tuple(m.shape) for m in seg_maps]
+    views = ops.make_views(cameras, shapes, image_sizes)
+    total = int(sum(h * w for h, w in shapes))
+    staged = torch.empty(total, dtype=torch.int32, device=device)
+    off = 0
+    for m, (h, w) in zip(seg_maps, shapes):
+        src = m if isinstance(m, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(m, np.int32))
+        staged[off:off + h * w].copy_(src.reshape(-1), non_blocking=True)
+        off += h * w
+    if label_min is None or n_classes is None:
+        label_min, n_classes = ops.DEFAULT_LABEL_MIN, ops.DEFAULT_N_CLASSES
+        if total:
+            lo, hi = ops.label_range(staged)
+            if lo < label_min or hi >= label_min + n_classes:
+                if hi - lo + 1 > ops.DEFAULT_N_CLASSES:
+                    raise ValueError(f"label maps span {hi - lo + 1} values; at most {ops.DEFAULT_N_CLASSES} are supported")
+                label_min, n_classes = lo, hi - lo + 1
+    packed = ops.pack_labels(staged, label_min, n_classes)
+    res = ops.lift_votes(pos, views, packed, label_min, n_classes, want_near=want_near, near_eps=near_eps)
+    if want_near:
+        return res[0].cpu().numpy(), res[1].cpu().numpy()
+    return res.cpu().numpy()
+
+
+def assign_labels(gaussians, cameras, input_dir, output_dir, model_type="mask2former", segmenter=None):
+    """Label every Gaussian by majority vote over its projections (reference :241-308).
+
+    Returns np.int32 [N]; -1 for Gaussians no view sees."""
+    upstream = None
+    used, maps, sizes = [], [], []
+    for camera in cameras:
+        img_path = os.path.join(input_dir, camera["img_name"] + ".png")
+        if not os.path.exists(img_path):
+            print(f"Warning: Image {camera['img_name']} not found")
+            continue
+        print(f"Processing image {os.path.basename(img_path)}...")
+        with Image.open(img_path) as image:
+            size = (image.size[0], image.size[1])
+        if segmenter is not None:
+            seg_map = segmenter(img_path, output_dir, model_type)
+        else:
+            seg_map = _precomputed_map(output_dir, camera["img_name"])
+            if seg_map is None:
+                if upstream is None:
+                    upstream = _UpstreamSegmenter(model_type)
+                seg_map = upstream(img_path, output_dir, model_type)
+        used.append(camera)
+        maps.append(np.asarray(seg_map))
+        sizes.append(size)
+    positions = np.ascontiguousarray(gaussians["position"], np.float32)
+    if not used:
+        return np.full(len(positions), -1, dtype=np.int32)
+    return lift_labels(positions, used, maps, sizes)
+
+
+def save_labeled_ply(output_file, plydata, labels):
+    """Write the input vertices plus an int32 `label` column as binary PLY (reference :311-332)."""
+    vertex = plyio.describe_with_label(plydata["vertex"].data, labels)
+    plyio.write_ply(output_file, [("vertex", vertex)], text=False)
+
+
+def main():
+    parser = argparse.ArgumentParser(description="Add labels to gaussians PLY file")
+    parser.add_argument("--ply_file", help="Input PLY file with gaussians data")
+    parser.add_argument("--camera_file", help="JSON file with camera data")
+    parser.add_argument("--input_dir", help="Directory containing input images")
+    parser.add_argument("--output_dir", help="Output directory to saved segmented input images")
+    parser.add_argument("--output_file", help="Output PLY file with labels")
+    parser.add_argument("--model", choices=["segformer", "mask2former", "yolo"], default="mask2former",
+                        help="Choose segmentation model: mask2former or yolo")
+    args = parser.parse_args()
+
+    print("Loading cameras...")
+    cameras = load_cameras(args.camera_file)
+    print("Loading gaussians...")
+    gaussians, plydata = load_gaussians(args.ply_file)
+    print("Assigning labels...")
+    labels = assign_labels(gaussians, cameras, args.input_dir, args.output_dir, model_type=args.model)
+    print("Saving labeled PLY file...")
+    save_labeled_ply(args.output_file, plydata, labels)
+    print(f"Done! Labeled PLY file saved as {args.output_file}")
+
+    values, counts = np.unique(labels, return_counts=True)
+    print("\nLabel statistics:")
+    print(f"Total gaussians: {len(labels)}")
+    print(f"Number of unique labels: {len(values)}")
+    print("Label counts:")
+    for value, count in zip(values, counts):
+        print(f"Label {value}: {count} gaussians ({100 * count / len(labels):.2f}%)")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,250 @@
+"""Host-side operators over libgslift.so.  PyTorch is used for device memory and streams only;
+every computation below is a call through the C ABI of include/gslift.h.
+
+Citations: dls = deep_learning_segmentation.py, km = 3D_clustering/k_means.py (reference).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from ._native import VIEW_DTYPE, check, lib
+
+DEFAULT_LABEL_MIN = -1      # YOLO background / Mask2Former "no segment" (dls:101)
+DEFAULT_N_CLASSES = 255     # codes 1..255; covers ADE20K (150) and COCO (80) ids plus -1
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must live on a CUDA device (there is no CPU path)")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class _Workspace:
+    """Per-device scratch tensor, grown on demand and reused across calls."""
+
+    def __init__(self):
+        self._buf = {}
+
+    def get(self, device: torch.device, nbytes: int) -> torch.Tensor:
+        key = (device.type, device.index)
+        buf = self._buf.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+            self._buf[key] = buf
+        return buf
+
+
+_ws = _Workspace()
+
+
+# --------------------------------------------------------------------------------------
+# lifting
+# --------------------------------------------------------------------------------------
+def make_views(cameras, map_shapes, image_sizes=None) -> np.ndarray:
+    """Camera dicts (cameras.json schema, dls:54-63) -> GslView table.
+
+    map_shapes[v] = (seg_h, seg_w) of view v's segmentation map (dls:267);
+    image_sizes[v] = (orig_w, orig_h) of the opened image (dls:263), default the map size.
+    `t` is evaluated with the reference's own expression `-R @ p` (dls:66) so it carries the
+    same rounding the reference would see on this host.  Maps are laid out back to back.
+    """
+    views = np.zeros(len(cameras), VIEW_DTYPE)
+    off = 0
+    for v, cam in enumerate(cameras):
+        R = np.array(cam["rotation"])
+        p = np.array(cam["position"])
+        seg_h, seg_w = (int(s) for s in map_shapes[v])
+        ow, oh = (seg_w, seg_h) if image_sizes is None else (int(s) for s in image_sizes[v])
+        rec = views[v]
+        rec["R"] = np.asarray(R, np.float64).reshape(9)
+        rec["t"] = -R @ p
+        rec["fx"], rec["fy"] = cam["fx"], cam["fy"]
+        rec["half_w"], rec["half_h"] = cam["width"] / 2, cam["height"] / 2
+        rec["width"], rec["height"] = cam["width"], cam["height"]
+        rec["scale_x"], rec["scale_y"] = seg_w / ow, seg_h / oh
+        rec["seg_w"], rec["seg_h"] = seg_w, seg_h
+        rec["map_offset"] = off
+        off += seg_h * seg_w
+    return views
+
+
+def pack_labels(maps: torch.Tensor, label_min: int = DEFAULT_LABEL_MIN,
+                n_classes: int = DEFAULT_N_CLASSES, out: torch.Tensor | None = None,
+                check_range: bool = True) -> torch.Tensor:
+    """int32 label maps (any shape, device) -> uint8 codes `label - label_min + 1`."""
+    _require_cuda(maps, "maps")
+    if maps.dtype != torch.int32:
+        raise TypeError("maps must be int32 (what segment_image returns, dls:158)")
+    n_px = maps.numel()
+    if out is None:
+        out = torch.empty(n_px, dtype=torch.uint8, device=maps.device)
+    err = torch.zeros(1, dtype=torch.int32, device=maps.device)
+    with torch.cuda.device(maps.device):
+        check(lib().gsl_pack_labels(maps.data_ptr(), out.data_ptr(), n_px, int(label_min),
+                                    int(n_classes), err.data_ptr(), _stream()))
+    if check_range and int(err.item()) != 0:
+        raise ValueError(f"label map value outside [{label_min}, {label_min + n_classes})")
+    return out
+
+
+def label_range(maps: torch.Tensor):
+    """(min, max) of an int32 device tensor, computed on the device."""
+    _require_cuda(maps, "maps")
+    mm = torch.tensor([2**31 - 1, -2**31], dtype=torch.int32, device=maps.device)
+    with torch.cuda.device(maps.device):
+        check(lib().gsl_label_range(maps.data_ptr(), maps.numel(), mm.data_ptr(), _stream()))
+    lo, hi = (int(v) for v in mm.tolist())
+    return lo, hi
+
+
+def lift_votes(pos: torch.Tensor, views: np.ndarray, packed: torch.Tensor,
+               label_min: int = DEFAULT_LABEL_MIN, n_classes: int = DEFAULT_N_CLASSES,
+               want_near: bool = False, near_eps: float = 1e-4, view_window: int = 0,
+               out: torch.Tensor | None = None):
+    """Vote loop + majority of assign_labels (dls:255-306) on precomputed, packed maps.
+
+    pos float32 [N,3] (device), views from make_views, packed uint8 (device).
+    Returns labels int32 [N] (device); with want_near also a uint8 [N] near-boundary mask.
+    """
+    _require_cuda(pos, "pos")
+    if pos.dtype != torch.float32 or pos.dim() != 2 or pos.shape[1] != 3:
+        raise TypeError("pos must be float32 [N, 3]")
+    views = np.ascontiguousarray(views)
+    if views.dtype != VIEW_DTYPE:
+        raise TypeError("views must come from make_views")
+    V = len(views)
+    if V:
+        _require_cuda(packed, "packed")
+        need = int((views["map_offset"] + views["seg_w"].astype(np.int64) * views["seg_h"]).max())
+        if packed.numel() < need:
+            raise ValueError(f"packed holds {packed.numel()} px, views address {need}")
+    N = pos.shape[0]
+    labels = out if out is not None else torch.empty(N, dtype=torch.int32, device=pos.device)
+    near = torch.empty(N, dtype=torch.uint8, device=pos.device) if want_near else None
+    L = lib()
+    nbytes = L.gsl_lift_workspace_bytes(N, V)
+    ws = _ws.get(pos.device, nbytes)
+    with torch.cuda.device(pos.device):
+        check(L.gsl_lift_votes(pos.data_ptr(), N, views.ctypes.data, V,
+                               packed.data_ptr() if V else None, int(label_min), int(n_classes),
+                               labels.data_ptr(), near.data_ptr() if want_near else None,
+                               float(near_eps), int(view_window), ws.data_ptr(), ws.numel(), _stream()))
+    return (labels, near) if want_near else labels
+
+
+def lift_phases(pos: torch.Tensor, views: np.ndarray, packed: torch.Tensor,
+                label_min: int = DEFAULT_LABEL_MIN, n_classes: int = DEFAULT_N_CLASSES,
+                view_window: int = 0, out: torch.Tensor | None = None):
+    """lift_votes as its two ABI phases.  Returns (run_gather, run_majority, labels): two
+    zero-argument callables that enqueue gsl_lift_gather / gsl_lift_majority on the current
+    stream (benchmarks put events between them)."""
+    _require_cuda(pos, "pos")
+    _require_cuda(packed, "packed")
+    views = np.ascontiguousarray(views)
+    N, V = pos.shape[0], len(views)
+    labels = out if out is not None else torch.empty(N, dtype=torch.int32, device=pos.device)
+    L = lib()
+    ws = _ws.get(pos.device, L.gsl_lift_workspace_bytes(N, V))
+
+    def run_gather():
+        check(L.gsl_lift_gather(pos.data_ptr(), N, views.ctypes.data, V, packed.data_ptr(), None, 0.0,
+                                int(view_window), ws.data_ptr(), ws.numel(), _stream()))
+
+    def run_majority():
+        check(L.gsl_lift_majority(N, V, int(label_min), int(n_classes), labels.data_ptr(),
+                                  ws.data_ptr(), ws.numel(), _stream()))
+
+    return run_gather, run_majority, labels
+
+
+# --------------------------------------------------------------------------------------
+# K-means
+# --------------------------------------------------------------------------------------
+def _check_kmeans(data: torch.Tensor, centroids: torch.Tensor):
+    _require_cuda(data, "data")
+    _require_cuda(centroids, "centroids")
+    if data.dtype != torch.float32 or centroids.dtype != torch.float32:
+        raise TypeError("data and centroids must be float32 (km:109)")
+    if data.dim() != 2 or centroids.dim() != 2 or data.shape[1] != centroids.shape[1]:
+        raise ValueError("data [N,D] and centroids [K,D] must agree on D")
+    return data.shape[0], data.shape[1], centroids.shape[0]
+
+
+def kmeans_assign(data: torch.Tensor, centroids: torch.Tensor, out: torch.Tensor | None = None):
+    """labels int32 [N]: nearest centroid, scipy-order float64 distance (km:116-122)."""
+    N, D, K = _check_kmeans(data, centroids)
+    labels = out if out is not None else torch.empty(N, dtype=torch.int32, device=data.device)
+    L = lib()
+    ws = _ws.get(data.device, L.gsl_kmeans_workspace_bytes(N, D, K))
+    with torch.cuda.device(data.device):
+        check(L.gsl_kmeans_assign(data.data_ptr(), N, D, centroids.data_ptr(), K, labels.data_ptr(),
+                                  ws.data_ptr(), ws.numel(), _stream()))
+    return labels
+
+
+def kmeans_step(data: torch.Tensor, centroids: torch.Tensor, labels: torch.Tensor | None = None,
+                sums: torch.Tensor | None = None):
+    """Assignment fused with per-cluster float64 sums/counts.  Returns (labels, sums[K,D+1])."""
+    N, D, K = _check_kmeans(data, centroids)
+    if labels is None:
+        labels = torch.empty(N, dtype=torch.int32, device=data.device)
+    if sums is None:
+        sums = torch.empty((K, D + 1), dtype=torch.float64, device=data.device)
+    L = lib()
+    ws = _ws.get(data.device, L.gsl_kmeans_workspace_bytes(N, D, K))
+    with torch.cuda.device(data.device):
+        check(L.gsl_kmeans_step(data.data_ptr(), N, D, centroids.data_ptr(), K, labels.data_ptr(),
+                                sums.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+    return labels, sums
+
+
+def kmeans_finalize(sums: torch.Tensor, old: torch.Tensor, new: torch.Tensor | None = None,
+                    shift: torch.Tensor | None = None):
+    """(new centroids f32 [K,D], shift f32 [1]) from reduced sums (km:125-131)."""
+    _require_cuda(sums, "sums")
+    _require_cuda(old, "old")
+    K, D = old.shape
+    if sums.dtype != torch.float64 or tuple(sums.shape) != (K, D + 1):
+        raise ValueError("sums must be float64 [K, D+1]")
+    if new is None:
+        new = torch.empty_like(old)
+    if shift is None:
+        shift = torch.empty(1, dtype=torch.float32, device=old.device)
+    with torch.cuda.device(old.device):
+        check(lib().gsl_kmeans_finalize(sums.data_ptr(), old.data_ptr(), K, D, new.data_ptr(),
+                                        shift.data_ptr(), _stream()))
+    return new, shift
+
+
+def kmeans_update_ordered(data: torch.Tensor, labels: torch.Tensor, old: torch.Tensor):
+    """Reference-order float32 sequential mean (km:125-128 bit for bit).  Single device."""
+    N, D, K = _check_kmeans(data, old)
+    _require_cuda(labels, "labels")
+    if labels.dtype != torch.int32 or labels.numel() != N:
+        raise TypeError("labels must be int32 [N]")
+    new = torch.empty_like(old)
+    shift = torch.empty(1, dtype=torch.float32, device=old.device)
+    L = lib()
+    ws = _ws.get(data.device, L.gsl_kmeans_workspace_bytes(N, D, K))
+    with torch.cuda.device(data.device):
+        check(L.gsl_kmeans_update_ordered(data.data_ptr(), labels.data_ptr(), N, D, K, old.data_ptr(),
+                                          new.data_ptr(), shift.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+    return new, shift
+
+
+def recolor(labels: torch.Tensor, palette: torch.Tensor, colors: torch.Tensor):
+    """colors[i] = palette[labels[i] % 8] in place (km:99-101, :147-149)."""
+    _require_cuda(labels, "labels")
+    _require_cuda(colors, "colors")
+    _require_cuda(palette, "palette")
+    if palette.dtype != torch.float32 or palette.numel() != 24 or colors.dtype != torch.float32:
+        raise TypeError("palette must be float32 [8,3], colors float32 [N,3]")
+    with torch.cuda.device(labels.device):
+        check(lib().gsl_recolor(labels.data_ptr(), labels.numel(), palette.data_ptr(), colors.data_ptr(), _stream()))
+    return colors

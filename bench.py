@@ -1,0 +1,421 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: Gaussian x view votes/s (label lifting) and K-means iters/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[3] + configs[4], the shape the metric is quoted on; it fits
+one GPU): 6M Gaussians x 300 views of 1920x1080 label maps with 151 label values, and K-means
+K=64 on 6M x 59 float32 features.  Total work is fixed; Gaussians (rows) are split across the
+ranks, every view is replicated ("scaling": "strong").  Data is synthetic (scene.py).
+
+One "step" = one lifting pass over this rank's Gaussians and all views (gsl_lift_gather +
+gsl_lift_majority) with positions and packed maps resident in HBM.  K-means iterations
+(gsl_kmeans_step + all-reduce + gsl_kmeans_finalize) are timed the same way and reported
+under "kmeans".  `e2e` is the same lifting through the public Python entry point
+(deep_learning_segmentation.lift_labels) with pinned HOST inputs: int32 maps and positions
+are copied to the device and labels copied back inside the timed region.
+
+`--impl reference` times the reference's CPU algorithm instead: the reference is pure Python
+and cannot be compiled, so this runs the oracle's C port of it (oracle/gsl_oracle.c, OpenMP,
+all host threads) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PKG = "3d_gaussian_splatting_project_b200"
+
+METRIC = "gaussian_view_votes_per_s"
+UNIT = "votes/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["native", "reference"], default="native")
+    ap.add_argument("--gaussians", type=int, default=6_000_000)
+    ap.add_argument("--views", type=int, default=300)
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--kmeans-rows", type=int, default=6_000_000)
+    ap.add_argument("--kmeans-dim", type=int, default=59)
+    ap.add_argument("--kmeans-k", type=int, default=64)
+    ap.add_argument("--view-window", type=int, default=0)
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-kmeans", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(a):
+    return {
+        "workload": f"C4+C5: lift {a.gaussians} Gaussians x {a.views} views {a.width}x{a.height} (151 labels, 32px blocks); "
+                    f"k-means K={a.kmeans_k} on {a.kmeans_rows}x{a.kmeans_dim} f32",
+        "gaussians": a.gaussians, "views": a.views, "map": [a.height, a.width],
+        "kmeans": {"rows": a.kmeans_rows, "dim": a.kmeans_dim, "k": a.kmeans_k},
+        "partition": f"gaussian-slices x{a.gpus}, views replicated",
+        "l2": "inputs (label maps 622 MB + vote sheet) exceed the 126 MB L2; no explicit flush",
+    }
+
+
+def peak_hbm():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(name):
+    """DRAM bytes per launch from the committed ncu capture, if one exists."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path)).get(name)
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+
+    def summary(self, t0, t1):
+        sm, mx, reasons, power = [], [], set(), []
+        for ts, line in self.rows:
+            if ts < t0 or ts > t1 + 0.2:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[6]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": float(max(power))}
+
+
+# ----------------------------------------------------------------------------------------
+# synthetic scene
+# ----------------------------------------------------------------------------------------
+def build_scene(a, gs, pinned):
+    import torch
+    cams = gs.scene.lookat_cameras(a.views, width=a.width, height=a.height, seed=4)
+    pos = gs.scene.gaussian_cloud(a.gaussians, 1.5, seed=4)
+    shape = (a.views, a.height, a.width)
+    if pinned:
+        maps_t = torch.empty(shape, dtype=torch.int32, pin_memory=True)
+        maps = maps_t.numpy()
+    else:
+        maps_t, maps = None, np.empty(shape, np.int32)
+    gs.scene.block_label_maps(a.views, a.height, a.width, block=32, lo=-1, hi=149, seed=1000, out=maps)
+    return cams, pos, maps, maps_t
+
+
+# ----------------------------------------------------------------------------------------
+# reference arm: the oracle's C port of the reference algorithm on the host cores
+# ----------------------------------------------------------------------------------------
+def cpu_lift_sample(a, orc, cams, pos, maps, budget_pairs=2.0e8):
+    n_s = int(min(len(pos), max(1000, budget_pairs // a.views)))
+    views = orc.make_views(cams, [(a.height, a.width)] * a.views)
+    t0 = time.perf_counter()
+    _, _, vis = orc.lift_votes(pos[:n_s], views, maps)
+    dt = time.perf_counter() - t0
+    return n_s * a.views / dt, dt, n_s, vis
+
+
+def cpu_kmeans_sample(a, orc, gs, rows=400_000):
+    rows = min(rows, a.kmeans_rows)
+    data = gs.scene.blob_features(rows, a.kmeans_dim, n_blobs=64, seed=5)
+    cen = data[np.random.default_rng(0).choice(rows, a.kmeans_k, replace=False)]
+    t0 = time.perf_counter()
+    lab = orc.kmeans_assign(data, cen)
+    orc.kmeans_update(data, lab, cen)
+    dt = time.perf_counter() - t0
+    return 1.0 / (dt * a.kmeans_rows / rows), dt, rows
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    gs = importlib.import_module(PKG)
+    orc.build()
+    cores = orc.max_threads()
+    cams, pos, maps, _ = build_scene(a, gs, pinned=False)
+    for _ in range(min(a.warmup, 1)):
+        cpu_lift_sample(a, orc, cams, pos, maps, budget_pairs=2.0e7)
+    rates, times = [], []
+    for _ in range(a.steps):
+        r, dt, n_s, _ = cpu_lift_sample(a, orc, cams, pos, maps)
+        rates.append(r); times.append(dt)
+    value = float(np.sum([n_s * a.views] * len(times)) / np.sum(times))
+    k_rate, k_dt, k_rows = cpu_kmeans_sample(a, orc, gs)
+    sample = f"lifting: first {n_s} of {a.gaussians} Gaussians x all {a.views} views per step; k-means: {k_rows} of {a.kmeans_rows} rows, 1 iteration, time scaled to full size"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": float(np.mean(times) * 1e3 * a.gaussians / n_s), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(a),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "kmeans": {"metric": "kmeans_iters_per_s", "value": k_rate, "unit": "iters/s", "cores": cores},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference is pure Python (12 us per pair measured, BASELINE.md); this arm is the oracle's C/OpenMP port of the same algorithm",
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------
+# native arm
+# ----------------------------------------------------------------------------------------
+def run_native(a):
+    import torch
+    import torch.distributed as dist
+    gs = importlib.import_module(PKG)
+    ops, sharding, dls, km = gs.ops, gs.sharding, gs.deep_learning_segmentation, gs.k_means
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the native arm has no CPU path")
+    rank, world, local = sharding.init_from_env("nccl")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world != a.gpus:
+        raise SystemExit(f"--gpus {a.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {a.gpus}")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    cams, pos, maps, maps_pinned = build_scene(a, gs, pinned=True)
+    lo, hi = sharding.slice_bounds(a.gaussians, rank, world)
+    n_r = hi - lo
+    H, W, V = a.height, a.width, a.views
+    views = ops.make_views(cams, [(H, W)] * V)
+
+    # ---- resident inputs: positions slice + packed maps (staged 8 views at a time)
+    d_pos = torch.from_numpy(pos[lo:hi]).to(dev)
+    packed = torch.empty(V * H * W, dtype=torch.uint8, device=dev)
+    pack_ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    pack_ms = 0.0
+    for v0 in range(0, V, 8):
+        v1 = min(v0 + 8, V)
+        chunk = maps_pinned[v0:v1].to(dev, non_blocking=True)
+        pack_ev[0].record()
+        ops.pack_labels(chunk, out=packed[v0 * H * W:v1 * H * W], check_range=False)
+        pack_ev[1].record()
+        torch.cuda.synchronize()
+        pack_ms += pack_ev[0].elapsed_time(pack_ev[1])
+        del chunk
+    run_gather, run_majority, labels = ops.lift_phases(d_pos, views, packed, view_window=a.view_window)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+
+    # ---- lifting, device resident
+    for _ in range(a.warmup):
+        run_gather(); run_majority()
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * a.steps)]
+    t_wall0 = time.time()
+    for i in range(a.steps):
+        ev[3 * i].record(); run_gather()
+        ev[3 * i + 1].record(); run_majority()
+        ev[3 * i + 2].record()
+    barrier()
+    t_wall1 = time.time()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    gather_ms = float(np.mean([ev[3 * i].elapsed_time(ev[3 * i + 1]) for i in range(a.steps)]))
+    major_ms = float(np.mean([ev[3 * i + 1].elapsed_time(ev[3 * i + 2]) for i in range(a.steps)]))
+    total_ms = sharding.barrier_max_ms(total_ms, dev)
+    ms_per_step = total_ms / a.steps
+    value = a.gaussians * V / (ms_per_step * 1e-3)
+    n_gather_launches = (V + 367) // 368
+    label_hist = torch.bincount((labels + 1).clamp(min=0).long(), minlength=152)[:3].tolist()
+
+    # ---- K-means, device resident
+    kres = None
+    if not a.skip_kmeans:
+        klo, khi = sharding.slice_bounds(a.kmeans_rows, rank, world)
+        feats = gs.scene.blob_features(a.kmeans_rows, a.kmeans_dim, n_blobs=64, seed=5)
+        np.random.seed(0)
+        init = feats[np.random.choice(a.kmeans_rows, a.kmeans_k, replace=False)]
+        feats_pinned = torch.from_numpy(feats[klo:khi]).pin_memory()
+        d_feats = feats_pinned.to(dev)
+        d_cen = torch.from_numpy(init).to(dev)
+        k_labels = torch.empty(khi - klo, dtype=torch.int32, device=dev)
+        sums = torch.empty((a.kmeans_k, a.kmeans_dim + 1), dtype=torch.float64, device=dev)
+        new_c, shift = torch.empty_like(d_cen), torch.empty(1, dtype=torch.float32, device=dev)
+
+        def k_iter(cen):
+            ops.kmeans_step(d_feats, cen, k_labels, sums)
+            if world > 1:
+                dist.all_reduce(sums)
+            ops.kmeans_finalize(sums, cen, new_c, shift)
+
+        for _ in range(a.warmup):
+            k_iter(d_cen)
+        barrier()
+        kev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ksteps = max(a.steps, 5)
+        cur = d_cen.clone()
+        kev[0].record()
+        for _ in range(ksteps):
+            k_iter(cur)
+            cur.copy_(new_c)                       # real Lloyd iterations: centroids move
+        kev[1].record()
+        barrier()
+        k_ms = sharding.barrier_max_ms(kev[0].elapsed_time(kev[1]), dev) / ksteps
+        peak, peak_src = peak_hbm()
+        rows_r = khi - klo
+        k_bytes = rows_r * (4 * a.kmeans_dim + 4) + 2 * a.kmeans_k * a.kmeans_dim * 4
+        kres = {"metric": "kmeans_iters_per_s", "value": 1e3 / k_ms, "unit": "iters/s", "ms_per_iter": k_ms,
+                "update": "fast (float64 segmented sums" + (", NCCL all-reduce of K x (D+1) f64)" if world > 1 else ")"),
+                "roofline": {"bound": "hbm", "achieved": k_bytes / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": k_bytes / (k_ms * 1e-3) / 1e9 / peak, "traffic": ncu_traffic("kmeans_step_kernel"),
+                             "algorithmic_bytes": k_bytes, "peak_source": peak_src},
+                "gpu_launches_per_iter": 3}
+        if world == 1:
+            # reference-order (bit-exact) update, single device
+            oev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            ops.kmeans_assign(d_feats, d_cen, k_labels); ops.kmeans_update_ordered(d_feats, k_labels, d_cen)
+            torch.cuda.synchronize()
+            oev[0].record()
+            for _ in range(3):
+                ops.kmeans_assign(d_feats, d_cen, k_labels)
+                ops.kmeans_update_ordered(d_feats, k_labels, d_cen)
+            oev[1].record(); torch.cuda.synchronize()
+            kres["ordered_ms_per_iter"] = oev[0].elapsed_time(oev[1]) / 3
+        if not a.skip_e2e:
+            barrier()
+            t0 = time.perf_counter()
+            dd = feats_pinned.to(dev, non_blocking=True)
+            cen_e, lab_e, it_e = km.lloyd(dd, d_cen, max_iter=5, tol=0.0, update="fast", verbose=False)
+            lab_host = lab_e.cpu()
+            barrier()
+            dt = time.perf_counter() - t0
+            dt = sharding.barrier_max_ms(dt * 1e3, dev) * 1e-3
+            kres["e2e"] = {"value": 5 / dt, "unit": "iters/s", "call": "k_means.lloyd(max_iter=5) incl. H2D rows + final assignment + D2H labels",
+                           "h2d_bytes_per_call": int(feats_pinned.numel() * 4 * 1), "d2h_bytes_per_call": int(lab_host.numel() * 4)}
+            del dd
+        del d_feats, feats_pinned, feats
+
+    if rank == 0:
+        sampler.stop()
+    clocks = sampler.summary(t_wall0, t_wall1) if rank == 0 else None
+
+    # ---- e2e lifting: public entry point, pinned host inputs, copies inside the timed region
+    e2e = None
+    if not a.skip_e2e:
+        pos_pinned = torch.from_numpy(pos[lo:hi]).pin_memory()
+        seg_list = [maps_pinned[v] for v in range(V)]
+        steps_e = max(2, min(a.steps, 3))
+        got = None
+        for i in range(1 + steps_e):
+            if i == 1:
+                barrier()
+                t0 = time.perf_counter()
+            got = dls.lift_labels(pos_pinned, cams, seg_list, None, device=dev)
+        barrier()
+        dt = (time.perf_counter() - t0) / steps_e
+        dt = sharding.barrier_max_ms(dt * 1e3, dev) * 1e-3
+        assert np.array_equal(got, labels.cpu().numpy()), "e2e labels differ from the device-resident run"
+        maps_bytes = int(maps.nbytes) * world          # every rank uploads every view (replicated)
+        e2e = {"value": a.gaussians * V / dt, "unit": UNIT, "ms_per_step": dt * 1e3,
+               "h2d_bytes_per_step": maps_bytes + a.gaussians * 12, "d2h_bytes_per_step": a.gaussians * 4,
+               "call": "deep_learning_segmentation.lift_labels(positions, cameras, seg_maps) with pinned host int32 maps"}
+
+    # ---- CPU baseline (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not a.skip_cpu:
+        from oracle import oracle as orc
+        r, dt, n_s, vis = cpu_lift_sample(a, orc, cams, pos, maps)
+        cpu = {"value": r, "unit": UNIT, "cores": orc.max_threads(), "kind": "port",
+               "sample": f"first {n_s} Gaussians x all {V} views ({dt:.1f} s of C/OpenMP oracle)"}
+        want, _, _ = orc.lift_votes(pos[:n_s], orc.make_views(cams, [(H, W)] * V), maps)
+        cpu["labels_match_gpu"] = bool(np.array_equal(want, labels[:n_s].cpu().numpy())) if lo == 0 else None
+        if kres is not None:
+            kr, kdt, krows = cpu_kmeans_sample(a, orc, gs)
+            kres["cpu_baseline"] = {"value": kr, "unit": "iters/s", "cores": orc.max_threads(), "kind": "port",
+                                    "sample": f"{krows} rows, 1 iteration ({kdt:.1f} s), time scaled to {a.kmeans_rows} rows"}
+
+    if rank == 0:
+        peak, peak_src = peak_hbm()
+        alg_bytes = 16 * n_r + V * H * W
+        ach = alg_bytes / (gather_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(a),
+            "kernels_ms": {"lift_gather_kernel": gather_ms, "lift_majority_kernel": major_ms, "pack_labels_kernel_total_untimed_stage": pack_ms},
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": ncu_traffic("lift_gather_kernel"), "kernel": "lift_gather_kernel",
+                         "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
+                         "note": "algorithmic bytes = 16 N_r + 1 V H W (SURVEY 8d, uint8 maps); the kernel is FP64-issue / L1-gather limited, see DESIGN.md"},
+            "cpu_baseline": cpu, "e2e": e2e, "kmeans": kres,
+            "gpu_launches": a.steps * (n_gather_launches + 1),
+            "clocks": clocks, "label_histogram_head": label_hist,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_native(a)
+
+
+if __name__ == "__main__":
+    main()

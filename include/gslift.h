@@ -1,0 +1,170 @@
+/*
+ * gslift.h -- C ABI of libgslift.so: B200 (sm_100a) label lifting and K-means labelling.
+ *
+ * The reference (GloireLINVANI/3D_Gaussian_Splatting_Project) is pure Python and has no
+ * FFI; its seam for this path is function level.  Each entry point below names the
+ * reference lines it replaces (paths relative to the reference root):
+ *
+ *   dls = deep_learning_segmentation.py      km = 3D_clustering/k_means.py
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer owned by the caller unless the
+ *     parameter is documented "host".  The library never allocates device memory: scratch
+ *     comes from the caller (`*_workspace_bytes`).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All work
+ *     is enqueued on it; no entry point synchronises the device.
+ *   - return 0 on success, a negative GSL_E* code otherwise; gsl_last_error() then returns
+ *     a thread-local message.  Nothing throws, nothing calls exit().
+ *   - gsl_lift_votes keeps the camera table in __constant__ memory: calls on ONE device must
+ *     be issued from one stream at a time (one stream per rank, one rank per GPU).
+ *   - there is no CPU fallback: without a CUDA device every compute entry fails with
+ *     GSL_ECUDA.
+ */
+#ifndef GSLIFT_H
+#define GSLIFT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSL_ABI_VERSION 1
+
+#define GSL_OK        0
+#define GSL_EINVAL   -1   /* bad argument (NULL pointer, negative size, V/K/D out of range) */
+#define GSL_EWORKSPACE -2 /* workspace too small                                            */
+#define GSL_ECUDA    -3   /* CUDA runtime error (message carries cudaGetErrorString)        */
+#define GSL_ERANGE   -4   /* label value outside the packable range                         */
+
+#define GSL_MAX_VIEWS   65535   /* view index is kept in 16 bits by the majority kernel      */
+#define GSL_MAX_CODES   255     /* distinct label values per call (uint8 code 0 = "no vote") */
+#define GSL_KMEANS_MAX_K 1024
+#define GSL_KMEANS_MAX_D 256
+
+/*
+ * One camera view, host side.  Everything project_gaussian (dls:43-82) and the rescale in
+ * assign_labels (dls:261-286) read, already in float64 exactly as Python would hold it.
+ */
+typedef struct GslView {
+    double R[9];       /* camera["rotation"] row-major, NOT transposed            dls:60    */
+    double t[3];       /* -R @ camera["position"], computed by the caller          dls:66    */
+    double fx, fy;     /*                                                          dls:54-55 */
+    double half_w;     /* camera["width"] / 2                                      dls:76    */
+    double half_h;     /* camera["height"] / 2                                     dls:77    */
+    double width;      /* camera["width"], camera["height"]: bounds test           dls:80    */
+    double height;
+    double scale_x;    /* seg_width / orig_width   (orig = opened image size)      dls:271   */
+    double scale_y;    /* seg_height / orig_height                                 dls:270   */
+    int32_t seg_w;     /* seg_map.shape[1]                                         dls:267   */
+    int32_t seg_h;     /* seg_map.shape[0]                                                   */
+    int64_t map_offset;/* element offset of this view's [seg_h][seg_w] map in `maps`         */
+} GslView;             /* 176 bytes */
+
+/* ABI version (GSL_ABI_VERSION of the built library). */
+int gsl_version(void);
+
+/* Message for the last non-zero return on this thread ("" if none). */
+const char *gsl_last_error(void);
+
+/* Number of CUDA devices visible to the library, or a negative error code. */
+int gsl_device_count(void);
+
+/*
+ * Stage label maps: int32 values as segment_image returns them (dls:158, :124) -> uint8
+ * codes  code = label - label_min + 1  (0 is reserved for "not visible").
+ * Values outside [label_min, label_min + n_classes) set *d_err (device int, caller zeroes
+ * it) to 1 and are written as code 0.  n_classes <= GSL_MAX_CODES.
+ */
+int gsl_pack_labels(const int32_t *maps, uint8_t *packed, int64_t n_px,
+                    int label_min, int n_classes, int *d_err, void *stream);
+
+/* Device min/max of an int32 buffer into d_minmax[2] (caller initialises to INT_MAX,
+ * INT_MIN); lets the host choose label_min / n_classes without a CPU pass. */
+int gsl_label_range(const int32_t *maps, int64_t n_px, int *d_minmax, void *stream);
+
+/* Scratch needed by gsl_lift_votes for N Gaussians and V views. */
+size_t gsl_lift_workspace_bytes(int64_t N, int V);
+
+/*
+ * The vote loop and the majority of assign_labels (dls:255-306) for precomputed maps:
+ * for every Gaussian, every view in order: project (dls:43-82, float64), test z > 0 and
+ * image bounds, rescale + clamp (dls:281-286), gather the code, count; then
+ * labels[i] = the label with the most votes, the one seen first in view order on a tie
+ * (Python max() over an insertion-ordered dict, dls:303), or -1 if never visible (dls:306).
+ *
+ *   pos        float32 [N][3]         gaussians['position'] (dls:36-38)
+ *   views      HOST array of V views in camera order, views whose image is missing already
+ *              dropped (dls:257-259).  Copied during the call.
+ *   packed     uint8 codes from gsl_pack_labels, view v at packed + views[v].map_offset
+ *   label_min, n_classes   the pair the maps were packed with
+ *   labels     int32 [N] out
+ *   near       optional uint8 [N] out (may be NULL): 1 when some (Gaussian, view) has an
+ *              image coordinate within near_eps px of an integer or |z_cam| < near_eps --
+ *              the set exempt from bit-exactness in the parity criterion.
+ *   view_window  views swept per pass over the Gaussians (0 = library default); results do
+ *              not depend on it.
+ */
+int gsl_lift_votes(const float *pos, int64_t N, const GslView *views, int V,
+                   const uint8_t *packed, int label_min, int n_classes, int32_t *labels,
+                   uint8_t *near, double near_eps, int view_window,
+                   void *ws, size_t ws_bytes, void *stream);
+
+/*
+ * The two phases of gsl_lift_votes, separately callable (same arguments, same workspace):
+ * gather fills the vote sheet in `ws` (one uint8 code per (Gaussian, view)), majority reduces
+ * it to labels.  gsl_lift_votes == gather then majority on the same stream.
+ */
+int gsl_lift_gather(const float *pos, int64_t N, const GslView *views, int V,
+                    const uint8_t *packed, uint8_t *near, double near_eps, int view_window,
+                    void *ws, size_t ws_bytes, void *stream);
+int gsl_lift_majority(int64_t N, int V, int label_min, int n_classes, int32_t *labels,
+                      const void *ws, size_t ws_bytes, void *stream);
+
+/* Scratch needed by the K-means entry points. */
+size_t gsl_kmeans_workspace_bytes(int64_t N, int D, int K);
+
+/*
+ * Assignment (km:116-122, :140-144): labels[i] = argmin_k d2(centroids[k], data[i]) with
+ * scipy cKDTree's float64 squared distance (four running lanes, no FMA).  Exact ties
+ * resolve to the lowest k.
+ *   data float32 [N][D] row-major (km:109), centroids float32 [K][D], labels int32 [N].
+ */
+int gsl_kmeans_assign(const float *data, int64_t N, int D, const float *centroids, int K,
+                      int32_t *labels, void *ws, size_t ws_bytes, void *stream);
+
+/*
+ * One Lloyd pass over this rank's rows: assignment as above, fused with per-cluster
+ * float64 sums and counts.  sums[K][D+1] (float64, out, overwritten): sums[k][0..D) = sum
+ * of member rows, sums[k][D] = member count.  Deterministic (fixed reduction order).
+ * Multi-GPU: all-reduce(sum) `sums` across ranks, then call gsl_kmeans_finalize.
+ */
+int gsl_kmeans_step(const float *data, int64_t N, int D, const float *centroids, int K,
+                    int32_t *labels, double *sums, void *ws, size_t ws_bytes, void *stream);
+
+/*
+ * Update + convergence metric (km:125-131) from reduced sums: new[k] = float32(sum/count),
+ * or old[k] when the cluster is empty; *shift = ||new - old||_F as float32 (device scalar).
+ */
+int gsl_kmeans_finalize(const double *sums, const float *old_centroids, int K, int D,
+                        float *new_centroids, float *shift, void *stream);
+
+/*
+ * Reference-order update (km:125-128 exactly): every centroid coordinate is the float32
+ * SEQUENTIAL sum of its members in index order, divided in float64 and rounded to float32
+ * -- what NumPy's mean(axis=0) produces.  Single device only (the order cannot be sharded).
+ *   labels int32 [N] from gsl_kmeans_assign / gsl_kmeans_step.
+ */
+int gsl_kmeans_update_ordered(const float *data, const int32_t *labels, int64_t N, int D, int K,
+                              const float *old_centroids, float *new_centroids, float *shift,
+                              void *ws, size_t ws_bytes, void *stream);
+
+/* Recolouring (km:99-101, :147-149): colors[i][0..3) = palette[labels[i] % 8]; `palette` is a
+ * device float32 [8][3] the host fills with COLORS (km:8), divided by 255.0 or not. */
+int gsl_recolor(const int32_t *labels, int64_t N, const float *palette, float *colors, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSLIFT_H */

@@ -1,0 +1,80 @@
+"""The C-ABI library: loads, exports every symbol include/gslift.h declares, fails loudly
+without a device.  No compute calls here (no GPU on the CPU runner)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from util import pkg
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "gslift.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(gsl_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_is_built_and_exports_every_declared_symbol():
+    native = pkg("_native")
+    assert os.path.exists(native.LIB_PATH), "run __graft_entry__.build() first"
+    raw = ctypes.CDLL(native.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 12
+    for name in names:
+        assert hasattr(raw, name), f"{name} declared in gslift.h but not exported"
+    assert sorted(native.SIGNATURES) == names, "ctypes SIGNATURES out of step with gslift.h"
+
+
+def test_version_and_view_struct_size():
+    native = pkg("_native")
+    assert native.lib().gsl_version() == 1
+    hdr = open(os.path.join(ROOT, "include", "gslift.h")).read()
+    assert "176 bytes" in hdr and native.VIEW_DTYPE.itemsize == 176
+
+
+def test_workspace_queries_are_host_only():
+    L = pkg("_native").lib()
+    assert L.gsl_lift_workspace_bytes(0, 0) >= 0
+    n = L.gsl_lift_workspace_bytes(1000, 10)
+    assert n >= 3 * 1024 * 4                     # ceil(10/4) words x Npad(1024) x 4 B
+    assert L.gsl_lift_workspace_bytes(1000, 300) > n
+    assert L.gsl_kmeans_workspace_bytes(100000, 59, 64) >= 64 * 60 * 8
+
+
+def test_argument_validation_needs_no_device():
+    native = pkg("_native")
+    L = native.lib()
+    assert L.gsl_pack_labels(None, None, 10, -1, 255, None, None) == -1
+    assert b"null" in L.gsl_last_error()
+    assert L.gsl_lift_votes(None, -1, None, 0, None, -1, 255, None, None, 0.0, 0, None, 0, None) == -1
+    assert L.gsl_kmeans_assign(None, 10, 0, None, 4, None, None, 0, None) == -1
+    assert L.gsl_kmeans_assign(None, 10, 3, None, 4000, None, None, 0, None) == -1
+    with pytest.raises(native.GslError):
+        native.check(L.gsl_kmeans_finalize(None, None, 4, 3, None, None, None))
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    ops = pkg("ops")
+    L = pkg("_native").lib()
+    assert L.gsl_device_count() == -3            # GSL_ECUDA, with a message
+    assert L.gsl_last_error()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.lift_votes(torch.zeros(4, 3), ops.make_views([], []), torch.zeros(0, dtype=torch.uint8))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.kmeans_assign(torch.zeros(4, 3), torch.zeros(2, 3))
+
+
+def test_product_never_imports_the_oracle():
+    pkg_dir = os.path.join(ROOT, "3d_gaussian_splatting_project_b200")
+    for dirpath, _, files in os.walk(pkg_dir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+                assert "libgsl_oracle" not in text, f

@@ -1,0 +1,170 @@
+"""Parity of the CUDA lifting path (through the C ABI) with the oracle and the reference's
+golden vectors.  Bar: labels bit-exact; the only tolerated differences are Gaussians with a
+projection within 1e-4 px of a pixel boundary (north_star), whose count is reported."""
+import contextlib
+import io
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from util import LIFT_CASES, load_lift_case, pkg
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def gpu_lift(pos, cameras, maps_list, sizes, **kw):
+    ops = pkg("ops")
+    shapes = [m.shape for m in maps_list]
+    views = ops.make_views(cameras, shapes, sizes)
+    flat = np.concatenate([np.ascontiguousarray(m, np.int32).reshape(-1) for m in maps_list]) if maps_list else np.zeros(0, np.int32)
+    packed = ops.pack_labels(torch.from_numpy(flat).to(DEV))
+    res = ops.lift_votes(torch.from_numpy(np.ascontiguousarray(pos, np.float32)).to(DEV), views, packed, **kw)
+    torch.cuda.synchronize()
+    return res
+
+
+def compare(got, want, near=None):
+    bad = got != want
+    if near is not None:
+        outside = bad & (near == 0)
+        assert not outside.any(), f"{outside.sum()} mismatches away from any pixel boundary"
+    else:
+        assert not bad.any(), f"{bad.sum()} of {len(want)} labels differ"
+    return int(bad.sum())
+
+
+@pytest.mark.parametrize("name", LIFT_CASES)
+def test_golden_vectors_from_the_verbatim_reference(name):
+    c = load_lift_case(name)
+    got = gpu_lift(c["pos"], c["cameras"], c["maps"], c["sizes"]).cpu().numpy()
+    assert got.dtype == np.int32
+    compare(got, c["labels"])
+
+
+@pytest.mark.parametrize("name", ["lift_lookat_regions", "lift_bundled_halfres"])
+def test_dropin_assign_labels_end_to_end(name, tmp_path):
+    """Through the reference-facing function: PNG probes, per-view prints, segmenter hook."""
+    from PIL import Image
+    dls = pkg("deep_learning_segmentation")
+    c = load_lift_case(name)
+    cams = [dict(cam) for cam in c["cameras"]]
+    by_name = {cam["img_name"]: i for i, cam in enumerate(cams)}
+    for cam, (w, h) in zip(cams, c["sizes"]):
+        Image.new("L", (w, h)).save(tmp_path / (cam["img_name"] + ".png"))
+    ghost = dict(cams[1], img_name="not_on_disk")          # skipped with a warning (dls:257-259)
+    cams_in = cams[:1] + [ghost] + cams[1:]
+    g = np.zeros(len(c["pos"]), dls.GAUSSIAN_DTYPE)
+    g["position"] = c["pos"]
+    seg = lambda path, out_dir, model_type: c["maps"][by_name[os.path.splitext(os.path.basename(path))[0]]]
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        labels = dls.assign_labels(g, cams_in, str(tmp_path), str(tmp_path / "out"), segmenter=seg)
+    lines = buf.getvalue().splitlines()
+    assert lines[1] == "Warning: Image not_on_disk not found"
+    assert sum(l.startswith("Processing image") for l in lines) == len(cams)
+    assert labels.dtype == np.int32
+    compare(labels, c["labels"])
+    # precomputed <img>_segmap.npy files (what the reference's segment_image leaves behind, dls:165)
+    os.makedirs(tmp_path / "pre", exist_ok=True)
+    for cam, m in zip(cams, c["maps"]):
+        np.save(tmp_path / "pre" / f"{cam['img_name']}_segmap.npy", m)
+    with contextlib.redirect_stdout(io.StringIO()):
+        labels2 = dls.assign_labels(g, cams, str(tmp_path), str(tmp_path / "pre"))
+    compare(labels2, c["labels"])
+
+
+def _scene(n, v, w, h, seed, block=16):
+    scene = pkg("scene")
+    cams = scene.lookat_cameras(v, width=w, height=h, seed=seed)
+    pos = scene.gaussian_cloud(n, 1.5, seed=seed + 1)
+    maps = scene.block_label_maps(v, h, w, block=block, seed=seed + 2)
+    return cams, pos, maps
+
+
+@pytest.mark.parametrize("n,v,w,h", [(1, 1, 64, 48), (31, 3, 64, 48), (1000, 5, 320, 200), (70001, 37, 640, 360), (300000, 24, 960, 540)])
+def test_random_scenes_against_oracle(oracle, n, v, w, h):
+    cams, pos, maps = _scene(n, v, w, h, seed=100 + v)
+    shapes = [(h, w)] * v
+    want, near, vis = oracle.lift_votes(pos, oracle.make_views(cams, shapes), maps, eps=1e-4, want_near=True)
+    got, gnear = gpu_lift(pos, cams, list(maps), None, want_near=True, near_eps=1e-4)
+    got, gnear = got.cpu().numpy(), gnear.cpu().numpy()
+    flips = compare(got, want, near)
+    assert np.array_equal(gnear, near), "near-boundary set differs from the oracle's"
+    print(f"[lift {n}x{v}] visible pairs {vis}, near-boundary Gaussians {int(near.sum())}, label flips {flips}")
+    assert flips == 0            # same dgemv formula on both sides: expect none even inside the band
+
+
+def test_view_window_and_chunking_do_not_change_results(oracle):
+    cams, pos, maps = _scene(5000, 11, 160, 90, seed=7)
+    base = gpu_lift(pos, cams, list(maps), None).cpu().numpy()
+    for win in (4, 8, 12, 64):
+        assert np.array_equal(gpu_lift(pos, cams, list(maps), None, view_window=win).cpu().numpy(), base)
+    # V > 368 exercises the second __constant__ chunk; many tiny maps
+    cams, pos, maps = _scene(3000, 401, 48, 32, seed=9, block=4)
+    want, _, _ = oracle.lift_votes(pos, oracle.make_views(cams, [(32, 48)] * 401), maps)
+    compare(gpu_lift(pos, cams, list(maps), None).cpu().numpy(), want)
+
+
+def test_rescaled_and_ragged_maps(oracle):
+    """Different seg-map size per view, image size != map size != camera size."""
+    scene = pkg("scene")
+    cams = scene.lookat_cameras(6, width=800, height=450, seed=21)
+    pos = scene.gaussian_cloud(20000, 1.5, seed=22)
+    shapes = [(450, 800), (225, 400), (100, 333), (450, 800), (77, 51), (900, 1600)]
+    sizes = [(800, 450), (800, 450), (640, 360), (400, 225), (800, 450), (800, 450)]
+    maps = [scene.block_label_map(h, w, 8, -1, 149, 300 + i) for i, (h, w) in enumerate(shapes)]
+    flat = np.concatenate([m.reshape(-1) for m in maps])
+    want, _, _ = oracle.lift_votes(pos, oracle.make_views(cams, shapes, sizes), flat)
+    compare(gpu_lift(pos, cams, maps, sizes).cpu().numpy(), want)
+
+
+def test_empty_inputs_and_label_range():
+    ops = pkg("ops")
+    cams, pos, maps = _scene(100, 2, 64, 48, seed=3)
+    out = gpu_lift(pos[:0], cams, list(maps), None)
+    assert out.numel() == 0
+    none = ops.lift_votes(torch.from_numpy(pos).to(DEV), ops.make_views([], []), torch.zeros(0, dtype=torch.uint8, device=DEV))
+    assert (none.cpu().numpy() == -1).all()            # no views: nothing visible (dls:306)
+    bad = torch.full((64,), 1000, dtype=torch.int32, device=DEV)
+    with pytest.raises(ValueError):
+        ops.pack_labels(bad)
+    assert ops.label_range(torch.tensor([5, -3, 77], dtype=torch.int32, device=DEV)) == (-3, 77)
+    dls, scene = pkg("deep_learning_segmentation"), pkg("scene")
+    maps0 = [scene.block_label_map(48, 64, 4, 0, 149, 50 + i) for i in range(2)]   # no -1 label
+    shifted = [m + 1000 for m in maps0]                # ids outside the default window: remapped
+    got = dls.lift_labels(pos, cams, shifted)
+    ref = dls.lift_labels(pos, cams, maps0)
+    assert (ref >= 0).any() and np.array_equal(np.where(ref == -1, -1, ref + 1000), got)
+
+
+def test_full_size_c3_properties_and_oracle(oracle):
+    """BASELINE config C3 shape (1M x 200 views, 1920x1080): slicing invariance (the multi-GPU
+    sharding property), permutation equivariance, determinism; and the oracle on a 1/8 slice."""
+    scene, ops = pkg("scene"), pkg("ops")
+    n, v, w, h = 1_000_000, 200, 1920, 1080
+    cams = scene.lookat_cameras(v, width=w, height=h, seed=3)
+    pos = scene.gaussian_cloud(n, 1.5, seed=3)
+    views = ops.make_views(cams, [(h, w)] * v)
+    packed = torch.empty(v * h * w, dtype=torch.uint8, device=DEV)
+    maps = scene.block_label_maps(v, h, w, block=32, seed=1000)
+    for v0 in range(0, v, 8):                          # stage + pack 8 maps at a time
+        ops.pack_labels(torch.from_numpy(maps[v0:v0 + 8]).to(DEV), out=packed[v0 * h * w:(v0 + 8) * h * w])
+    d_pos = torch.from_numpy(pos).to(DEV)
+    full = ops.lift_votes(d_pos, views, packed).cpu().numpy()
+    again = ops.lift_votes(d_pos, views, packed).cpu().numpy()
+    assert np.array_equal(full, again)
+    lo, hi = 375_000, 500_000                           # rank 3 of 8
+    part = ops.lift_votes(d_pos[lo:hi].contiguous(), views, packed).cpu().numpy()
+    assert np.array_equal(part, full[lo:hi])
+    perm = np.random.default_rng(0).permutation(n)
+    shuffled = ops.lift_votes(torch.from_numpy(pos[perm]).to(DEV), views, packed).cpu().numpy()
+    assert np.array_equal(shuffled, full[perm])
+    # oracle on the same slice, all 200 views
+    want, near, vis = oracle.lift_votes(pos[lo:hi], oracle.make_views(cams, [(h, w)] * v), maps, eps=1e-4, want_near=True)
+    flips = compare(part, want, near)
+    print(f"[C3 slice] {hi - lo} Gaussians x {v} views: visible pairs {vis} ({vis / ((hi - lo) * v):.1%}), "
+          f"near-boundary Gaussians {int(near.sum())}, flips {flips}")
+    assert flips == 0

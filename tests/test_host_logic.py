@@ -1,0 +1,146 @@
+"""Host-side logic that needs no GPU: view tables, PLY I/O, drop-in surfaces, sharding (gloo)."""
+import inspect
+import io
+import os
+import subprocess
+import sys
+import contextlib
+
+import numpy as np
+import pytest
+
+from util import load_lift_case, pkg
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_make_views_matches_oracle_table(oracle):
+    c = load_lift_case("lift_bundled_halfres")
+    mine = pkg("ops").make_views(c["cameras"], c["shapes"], c["sizes"])
+    ref = oracle.make_views(c["cameras"], c["shapes"], c["sizes"])
+    assert mine.dtype.itemsize == ref.dtype.itemsize == 176
+    for name in mine.dtype.names:
+        assert np.array_equal(mine[name], ref[name]), name     # incl. t = -R @ p, bit for bit
+    assert mine["scale_x"][0] == 1.0 and mine["width"][0] == 3114
+
+
+def test_ply_roundtrip_binary_and_ascii(tmp_path):
+    plyio, scene = pkg("plyio"), pkg("scene")
+    v = scene.standin_3dgs_vertices(257, seed=3)
+    labels = np.arange(257, dtype=np.int64) % 11 - 1
+    out = plyio.describe_with_label(v, labels)
+    assert out.dtype.names[-1] == "label" and out.dtype["label"] == np.dtype("<i4")
+    b, a = tmp_path / "b.ply", tmp_path / "a.ply"
+    plyio.write_ply(b, [("vertex", out)], text=False)
+    plyio.write_ply(a, [("vertex", out)], text=True)
+    head = open(b, "rb").read(4096).split(b"end_header\n")[0].decode().splitlines()
+    assert head[:3] == ["ply", "format binary_little_endian 1.0", "element vertex 257"]
+    assert head[3] == "property float x" and head[-1] == "property int label" and len(head) == 3 + 63
+    assert os.path.getsize(b) == len("\n".join(head)) + 1 + len("end_header\n") + 257 * 63 * 4
+    for path, text in ((b, False), (a, True)):
+        back = plyio.read_ply(path)
+        assert back.text == text
+        got = back["vertex"].data
+        assert got.dtype.names == out.dtype.names
+        for n in out.dtype.names:
+            assert np.array_equal(got[n], out[n]), n         # %.18g round-trips float32 exactly
+    first = open(a).read().split("end_header\n")[1].splitlines()[0].split()
+    assert len(first) == 63 and first[-1] == "-1"
+    assert first[0] == "%.18g" % float(v["x"][0])
+
+
+def test_dropin_surfaces_match_reference_signatures():
+    dls, km = pkg("deep_learning_segmentation"), pkg("k_means")
+    assert list(inspect.signature(dls.assign_labels).parameters)[:5] == ["gaussians", "cameras", "input_dir", "output_dir", "model_type"]
+    assert inspect.signature(dls.assign_labels).parameters["model_type"].default == "mask2former"
+    assert list(inspect.signature(dls.project_gaussian).parameters) == ["position", "camera"]
+    assert list(inspect.signature(dls.save_labeled_ply).parameters) == ["output_file", "plydata", "labels"]
+    p = inspect.signature(km.k_means_with_color).parameters
+    assert list(p)[:5] == ["points", "k", "colors", "max_iter", "tol"] and p["max_iter"].default == 100 and p["tol"].default == 1e-4
+    assert list(inspect.signature(km.k_means_kd_tree).parameters)[:5] == ["data", "k", "colors", "max_iter", "tol"]
+    assert len(km.COLORS) == 8 and km.COLORS[3] == [126, 24, 145]
+
+
+def test_project_gaussian_scalar_matches_oracle(oracle):
+    dls = pkg("deep_learning_segmentation")
+    c = load_lift_case("lift_lookat_fullres")
+    for i in range(0, 400, 7):
+        cam = c["cameras"][i % len(c["cameras"])]
+        assert dls.project_gaussian(c["pos"][i], cam) == oracle.project_py(c["pos"][i], cam)
+
+
+def test_assign_labels_skips_missing_images_like_the_reference(tmp_path):
+    dls = pkg("deep_learning_segmentation")
+    g = np.zeros(5, dls.GAUSSIAN_DTYPE)
+    cams = load_lift_case("lift_degenerate")["cameras"]
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        labels = dls.assign_labels(g, cams, str(tmp_path), str(tmp_path))
+    assert labels.dtype == np.int32 and np.array_equal(labels, np.full(5, -1))
+    assert buf.getvalue().splitlines() == [f"Warning: Image {c['img_name']} not found" for c in cams]
+
+
+def test_cli_flags_unchanged():
+    for script, flags in (("deep_learning_segmentation.py", ["--ply_file", "--camera_file", "--input_dir", "--output_dir", "--output_file", "--model"]),
+                          (os.path.join("3D_clustering", "k_means.py"), ["--file_path", "--save_path", "--k"])):
+        out = subprocess.run([sys.executable, os.path.join(ROOT, script), "--help"], capture_output=True, text=True, cwd=ROOT)
+        assert out.returncode == 0, out.stderr
+        for f in flags:
+            assert f in out.stdout
+
+
+def test_slice_bounds_partition():
+    sb = pkg("sharding").slice_bounds
+    for n in (0, 1, 7, 1000, 6_000_000):
+        for w in (1, 2, 3, 8):
+            cuts = [sb(n, r, w) for r in range(w)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == n
+            assert all(cuts[i][1] == cuts[i + 1][0] for i in range(w - 1))
+            sizes = [hi - lo for lo, hi in cuts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+_WORKER = r'''
+import os, sys, importlib
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from oracle import oracle as orc
+gs = importlib.import_module("3d_gaussian_splatting_project_b200")
+rank, world, _ = gs.sharding.init_from_env("gloo")
+# K-means exchange step on CPU tensors: per-rank float64 sums/counts from the oracle,
+# all-reduced, must equal the single-process sums; slices preserve index order.
+data = gs.scene.blob_features(5003, 7, n_blobs=5, seed=9)
+cen = data[:6].copy()
+lo, hi = gs.sharding.slice_bounds(len(data), rank, world)
+lab = orc.kmeans_assign(data[lo:hi], cen)
+sums = np.zeros((6, 8))
+for k in range(6):
+    m = lab == k
+    sums[k, :7] = data[lo:hi][m].astype(np.float64).sum(0); sums[k, 7] = m.sum()
+t = torch.from_numpy(sums); dist.all_reduce(t)
+full = orc.kmeans_assign(data, cen)
+assert np.array_equal(full[lo:hi], lab)
+want = np.zeros((6, 8))
+for k in range(6):
+    m = full == k
+    want[k, :7] = data[m].astype(np.float64).sum(0); want[k, 7] = m.sum()
+assert np.allclose(t.numpy(), want, rtol=1e-13, atol=0), np.abs(t.numpy() - want).max()
+got = gs.sharding.gather_labels(torch.from_numpy(lab.astype(np.int32)), len(data), rank, world)
+if rank == 0:
+    assert np.array_equal(got.numpy(), full.astype(np.int32))
+ms = gs.sharding.barrier_max_ms(float(rank + 1), "cpu")
+assert ms == world
+dist.barrier(); dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+def test_sharding_world_size_2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="2")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29731", str(script), ROOT],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert out.stdout.count("ok") == 2
