@@ -43,6 +43,7 @@ SIGNATURES = {
     "gsl_lift_votes": (_i32, [_vp, _i64, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _dbl, _i32, _vp, _sz, _vp]),
     "gsl_lift_gather": (_i32, [_vp, _i64, _vp, _i32, _vp, _vp, _dbl, _i32, _vp, _sz, _vp]),
     "gsl_lift_majority": (_i32, [_i64, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
+    "gsl_div_selftest": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "gsl_kmeans_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "gsl_kmeans_assign": (_i32, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _sz, _vp]),
     "gsl_kmeans_step": (_i32, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _sz, _vp]),

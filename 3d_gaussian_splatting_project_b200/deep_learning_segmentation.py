@@ -137,13 +137,13 @@ def lift_labels(positions, cameras, seg_maps, image_sizes=None, device=None, wan
         staged[off:off + h * w].copy_(src.reshape(-1), non_blocking=True)
         off += h * w
     if label_min is None or n_classes is None:
-        label_min, n_classes = ops.DEFAULT_LABEL_MIN, ops.DEFAULT_N_CLASSES
+        # tight code range from the data (device min/max): fewer histogram rows per Gaussian
+        label_min, n_classes = ops.DEFAULT_LABEL_MIN, 1
         if total:
             lo, hi = ops.label_range(staged)
-            if lo < label_min or hi >= label_min + n_classes:
-                if hi - lo + 1 > ops.DEFAULT_N_CLASSES:
-                    raise ValueError(f"label maps span {hi - lo + 1} values; at most {ops.DEFAULT_N_CLASSES} are supported")
-                label_min, n_classes = lo, hi - lo + 1
+            if hi - lo + 1 > ops.DEFAULT_N_CLASSES:
+                raise ValueError(f"label maps span {hi - lo + 1} values; at most {ops.DEFAULT_N_CLASSES} are supported")
+            label_min, n_classes = lo, hi - lo + 1
     packed = ops.pack_labels(staged, label_min, n_classes)
     res = ops.lift_votes(pos, views, packed, label_min, n_classes, want_near=want_near, near_eps=near_eps)
     if want_near:

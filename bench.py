@@ -248,12 +248,12 @@ def run_native(a):
         v1 = min(v0 + 8, V)
         chunk = maps_pinned[v0:v1].to(dev, non_blocking=True)
         pack_ev[0].record()
-        ops.pack_labels(chunk, out=packed[v0 * H * W:v1 * H * W], check_range=False)
+        ops.pack_labels(chunk, -1, 151, out=packed[v0 * H * W:v1 * H * W], check_range=False)
         pack_ev[1].record()
         torch.cuda.synchronize()
         pack_ms += pack_ev[0].elapsed_time(pack_ev[1])
         del chunk
-    run_gather, run_majority, labels = ops.lift_phases(d_pos, views, packed, view_window=a.view_window)
+    run_gather, run_majority, labels = ops.lift_phases(d_pos, views, packed, -1, 151, view_window=a.view_window)
 
     sampler = ClockSampler(local)
     if rank == 0:

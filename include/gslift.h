@@ -15,8 +15,8 @@
  *     is enqueued on it; no entry point synchronises the device.
  *   - return 0 on success, a negative GSL_E* code otherwise; gsl_last_error() then returns
  *     a thread-local message.  Nothing throws, nothing calls exit().
- *   - gsl_lift_votes keeps the camera table in __constant__ memory: calls on ONE device must
- *     be issued from one stream at a time (one stream per rank, one rank per GPU).
+ *   - entry points keep no global state (camera tables travel as kernel parameters), so calls
+ *     on distinct streams are independent.
  *   - there is no CPU fallback: without a CUDA device every compute entry fails with
  *     GSL_ECUDA.
  */
@@ -103,8 +103,8 @@ size_t gsl_lift_workspace_bytes(int64_t N, int V);
  *   near       optional uint8 [N] out (may be NULL): 1 when some (Gaussian, view) has an
  *              image coordinate within near_eps px of an integer or |z_cam| < near_eps --
  *              the set exempt from bit-exactness in the parity criterion.
- *   view_window  views swept per pass over the Gaussians (0 = library default); results do
- *              not depend on it.
+ *   view_window  views swept per launch over all Gaussians: <= 8 selects 8, anything else
+ *              (0 = default) 16; results do not depend on it.
  */
 int gsl_lift_votes(const float *pos, int64_t N, const GslView *views, int V,
                    const uint8_t *packed, int label_min, int n_classes, int32_t *labels,
@@ -121,6 +121,11 @@ int gsl_lift_gather(const float *pos, int64_t N, const GslView *views, int V,
                     void *ws, size_t ws_bytes, void *stream);
 int gsl_lift_majority(int64_t N, int V, int label_min, int n_classes, int32_t *labels,
                       const void *ws, size_t ws_bytes, void *stream);
+
+/* Test hook: counts (into *n_bad, device) the i for which the kernel's shared-reciprocal
+ * division of a1[i]/b[i], a2[i]/b[i] differs in any bit from IEEE-754 division. */
+int gsl_div_selftest(const double *a1, const double *a2, const double *b, int64_t n,
+                     unsigned long long *n_bad, void *stream);
 
 /* Scratch needed by the K-means entry points. */
 size_t gsl_kmeans_workspace_bytes(int64_t N, int D, int K);

@@ -97,12 +97,35 @@ def test_random_scenes_against_oracle(oracle, n, v, w, h):
     assert flips == 0            # same dgemv formula on both sides: expect none even inside the band
 
 
+def test_shared_reciprocal_division_is_ieee_exact():
+    """The gather kernel divides fx*X and fy*Y by Z with one shared reciprocal; the result
+    must equal IEEE-754 division bit for bit, on ordinary and on extreme operands."""
+    native = pkg("_native")
+    rng = np.random.default_rng(17)
+    n = 1 << 22
+    def draw(kind):
+        if kind == "scene":
+            return rng.standard_normal(n) * rng.choice([1e-3, 1.0, 50.0, 4000.0], n)
+        bits = rng.integers(0, 2**63, n, dtype=np.int64) | (rng.integers(0, 2, n, dtype=np.int64) << 63)
+        return bits.view(np.float64)
+    for kind in ("scene", "bits"):
+        a1, a2, b = draw(kind), draw(kind), draw(kind)
+        if kind == "bits":
+            b[:8] = [0.0, -0.0, np.inf, -np.inf, np.nan, 5e-324, 1e308, -1e-308]
+            a1[:8] = [1.0, 0.0, np.inf, 1.0, 1.0, 5e-324, 1e308, 1e308]
+        bad = torch.zeros(1, dtype=torch.int64, device=DEV)
+        t = [torch.from_numpy(x).to(DEV) for x in (a1, a2, b)]
+        native.check(native.lib().gsl_div_selftest(t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), n, bad.data_ptr(), None))
+        torch.cuda.synchronize()
+        assert int(bad.item()) == 0, f"{int(bad.item())} of {n} quotients differ from IEEE division ({kind})"
+
+
 def test_view_window_and_chunking_do_not_change_results(oracle):
     cams, pos, maps = _scene(5000, 11, 160, 90, seed=7)
     base = gpu_lift(pos, cams, list(maps), None).cpu().numpy()
     for win in (4, 8, 12, 64):
         assert np.array_equal(gpu_lift(pos, cams, list(maps), None, view_window=win).cpu().numpy(), base)
-    # V > 368 exercises the second __constant__ chunk; many tiny maps
+    # many windows, the last one partial (401 = 25 * 16 + 1); many tiny maps
     cams, pos, maps = _scene(3000, 401, 48, 32, seed=9, block=4)
     want, _, _ = oracle.lift_votes(pos, oracle.make_views(cams, [(32, 48)] * 401), maps)
     compare(gpu_lift(pos, cams, list(maps), None).cpu().numpy(), want)
