@@ -17,6 +17,8 @@
 //   kmeans_finalize_kernel    new = float32(sum / count) or old; shift = ||new - old||_F
 //
 // Compiled with -fmad=false (the distance must not be contracted).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace gsl {
@@ -27,17 +29,19 @@ constexpr int kStepWarps = kStepThreads / 32;
 struct StepSmem {
     // byte offsets into dynamic shared memory
     size_t tile, cent, acc, lab, total;
-    int pitch;   // row pitch of the tile in floats (odd -> conflict-free row-per-lane reads)
+    int pitch;    // row pitch of the tile in floats (odd -> conflict-free row-per-lane reads)
+    int cpitch;   // row pitch of the centroid block in floats (D, or DREG zero-padded)
 };
 
-static inline StepSmem step_layout(int D, int K, bool accumulate)
+static inline StepSmem step_layout(int D, int K, bool accumulate, int dreg)
 {
     StepSmem s;
     s.pitch = D | 1;
+    s.cpitch = dreg ? dreg : D;
     size_t o = 0;
     s.acc = o;  o += accumulate ? align_up((size_t)K * (D + 1) * sizeof(double), 16) : 0;
+    s.cent = o; o += align_up((size_t)K * s.cpitch * sizeof(float), 16);
     s.tile = o; o += align_up((size_t)kStepThreads * s.pitch * sizeof(float), 16);
-    s.cent = o; o += align_up((size_t)K * D * sizeof(float), 16);
     s.lab = o;  o += (size_t)kStepThreads * sizeof(int);
     s.total = o;
     return s;
@@ -63,11 +67,62 @@ __device__ __forceinline__ double sqdist_scipy(const float *__restrict__ c, cons
     return s;
 }
 
-template <bool kAccumulate>
+// Float32 screening distance: sum of fmaf((x-c), (x-c), s) over DREG zero-padded dims, the row
+// in registers, the centroid read as broadcast 16-byte shared loads.  Every partial sum is
+// non-negative, so the result is within (DREG + 3) ulp-relative of the real distance.
+template <int DREG>
+__device__ __forceinline__ float sqdist_screen(const float (&x)[DREG], const float *__restrict__ c)
+{
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < DREG; i += 4) {
+        const float4 cv = *reinterpret_cast<const float4 *>(c + i);
+        const float d0 = x[i] - cv.x, d1 = x[i + 1] - cv.y, d2 = x[i + 2] - cv.z, d3 = x[i + 3] - cv.w;
+        s0 = fmaf(d0, d0, s0); s1 = fmaf(d1, d1, s1); s0 = fmaf(d2, d2, s0); s1 = fmaf(d3, d3, s1);
+    }
+    return s0 + s1;
+}
+
+// Nearest centroid of one row, exactly as the float64 scan would find it (first minimum of the
+// scipy-order distance), at float32 cost: screen all K in float32, and only when the two
+// smallest screened distances are closer than the screening error can explain, evaluate the
+// float64 distance of the candidates inside the error band.
+template <int DREG>
+__device__ __forceinline__ int nearest_screened(const float *__restrict__ xrow, const float *__restrict__ cent,
+                                                int K, int D, float eps)
+{
+    float x[DREG];
+#pragma unroll
+    for (int i = 0; i < DREG; ++i) x[i] = i < D ? xrow[i] : 0.f;
+    float s1 = INFINITY, s2 = INFINITY;
+    int k1 = 0;
+    for (int k = 0; k < K; ++k) {
+        const float s = sqdist_screen<DREG>(x, cent + k * DREG);
+        if (s < s1) { s2 = s1; s1 = s; k1 = k; }
+        else if (s < s2) s2 = s;
+    }
+    // unique  <=>  every other real distance exceeds the smallest one even after both move by eps
+    const bool unique = (s2 * (1.f - eps) > s1 * (1.f + eps)) && (s1 > 1e-30f);
+    if (unique) return k1;
+    const float bound = s1 * (1.f + 2.f * eps);
+    double best = INFINITY;
+    int mine = 0;
+    for (int k = 0; k < K; ++k) {
+        const float s = sqdist_screen<DREG>(x, cent + k * DREG);
+        if (!(s * (1.f - 2.f * eps) <= bound) && (s1 > 1e-30f)) continue;     // outside the band
+        const double d2 = sqdist_scipy(cent + k * DREG, xrow, D);
+        if (d2 < best) { best = d2; mine = k; }
+    }
+    return mine;
+}
+
+// DREG = 0: float64 scan of every centroid (any D).  DREG > 0: float32 screening with the row
+// in DREG registers (D <= DREG), float64 only for near ties.  Both give identical labels.
+template <int DREG, bool kAccumulate>
 __global__ void __launch_bounds__(kStepThreads)
 kmeans_step_kernel(const float *__restrict__ data, int64_t N, int D, const float *__restrict__ centroids,
                    int K, int32_t *__restrict__ labels, double *__restrict__ partials,
-                   StepSmem L, int vec_ok)
+                   StepSmem L, int vec_ok, float eps)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     double *acc = reinterpret_cast<double *>(smem + L.acc);
@@ -75,9 +130,12 @@ kmeans_step_kernel(const float *__restrict__ data, int64_t N, int D, const float
     float *cent = reinterpret_cast<float *>(smem + L.cent);
     int *lab = reinterpret_cast<int *>(smem + L.lab);
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const int pitch = L.pitch;
+    const int pitch = L.pitch, cpitch = L.cpitch;
 
-    for (int i = t; i < K * D; i += kStepThreads) cent[i] = centroids[i];
+    for (int i = t; i < K * cpitch; i += kStepThreads) {
+        const int k = i / cpitch, d = i - k * cpitch;
+        cent[i] = d < D ? centroids[k * D + d] : 0.f;
+    }
     if (kAccumulate)
         for (int i = t; i < K * (D + 1); i += kStepThreads) acc[i] = 0.0;
 
@@ -113,11 +171,15 @@ kmeans_step_kernel(const float *__restrict__ data, int64_t N, int D, const float
         int mine = -1;
         if (t < rows) {
             const float *x = tile + t * pitch;
-            double best = sqdist_scipy(cent, x, D);
-            mine = 0;
-            for (int k = 1; k < K; ++k) {
-                const double d2 = sqdist_scipy(cent + k * D, x, D);
-                if (d2 < best) { best = d2; mine = k; }
+            if (DREG > 0) {
+                mine = nearest_screened<(DREG > 0 ? DREG : 4)>(x, cent, K, D, eps);
+            } else {
+                double best = sqdist_scipy(cent, x, D);
+                mine = 0;
+                for (int k = 1; k < K; ++k) {
+                    const double d2 = sqdist_scipy(cent + k * cpitch, x, D);
+                    if (d2 < best) { best = d2; mine = k; }
+                }
             }
             labels[row0 + t] = mine;
         }
@@ -229,17 +291,47 @@ extern "C" size_t gsl_kmeans_workspace_bytes(int64_t N, int D, int K)
     return step > ord ? step : ord;
 }
 
+// GSLIFT_KMEANS_EXACT=1 forces the float64 scan (the screening path must give the same labels).
+static bool force_exact()
+{
+    const char *e = getenv("GSLIFT_KMEANS_EXACT");
+    return e && e[0] == '1';
+}
+
+template <int DREG, bool kAcc>
+static int launch_step_t(const float *data, int64_t N, int D, const float *centroids, int K,
+                         int32_t *labels, double *partials, int grid, cudaStream_t st)
+{
+    const StepSmem L = step_layout(D, K, kAcc, DREG);
+    if (L.total > 227 * 1024) return fail(GSL_EINVAL, "kmeans: K=%d, D=%d needs %zu B of shared memory (> 227 KB)", K, D, L.total);
+    GSL_CUDA_TRY(cudaFuncSetAttribute(kmeans_step_kernel<DREG, kAcc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    const int vec_ok = (((uintptr_t)data & 15) == 0) && (((size_t)kStepThreads * D) % 4 == 0);
+    // screening error: (DREG + 3) roundings on non-negative partial sums, plus the float32
+    // products of the comparison itself; 2^-24 per rounding, generous margin.
+    const float eps = (float)((DREG + 12) * 5.9604644775390625e-08);
+    kmeans_step_kernel<DREG, kAcc><<<grid, kStepThreads, L.total, st>>>(data, N, D, centroids, K, labels, partials, L, vec_ok, eps);
+    GSL_LAUNCH_CHECK("kmeans_step_kernel");
+    return GSL_OK;
+}
+
 template <bool kAcc>
 static int launch_step(const float *data, int64_t N, int D, const float *centroids, int K,
                        int32_t *labels, double *partials, int grid, cudaStream_t st)
 {
-    const StepSmem L = step_layout(D, K, kAcc);
-    if (L.total > 227 * 1024) return fail(GSL_EINVAL, "kmeans: K=%d, D=%d needs %zu B of shared memory (> 227 KB)", K, D, L.total);
-    GSL_CUDA_TRY(cudaFuncSetAttribute(kmeans_step_kernel<kAcc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-    const int vec_ok = (((uintptr_t)data & 15) == 0) && (((size_t)kStepThreads * D) % 4 == 0);
-    kmeans_step_kernel<kAcc><<<grid, kStepThreads, L.total, st>>>(data, N, D, centroids, K, labels, partials, L, vec_ok);
-    GSL_LAUNCH_CHECK("kmeans_step_kernel");
-    return GSL_OK;
+    // the screened kernel pads the centroid block to DREG floats per row: fall back to the
+    // float64 scan when that does not fit or the row does not fit the register block
+    if (!force_exact() && D <= 64) {
+        const int dreg = D <= 8 ? 8 : D <= 16 ? 16 : D <= 32 ? 32 : 64;
+        if (step_layout(D, K, kAcc, dreg).total <= 227 * 1024) {
+            switch (dreg) {
+                case 8:  return launch_step_t<8, kAcc>(data, N, D, centroids, K, labels, partials, grid, st);
+                case 16: return launch_step_t<16, kAcc>(data, N, D, centroids, K, labels, partials, grid, st);
+                case 32: return launch_step_t<32, kAcc>(data, N, D, centroids, K, labels, partials, grid, st);
+                default: return launch_step_t<64, kAcc>(data, N, D, centroids, K, labels, partials, grid, st);
+            }
+        }
+    }
+    return launch_step_t<0, kAcc>(data, N, D, centroids, K, labels, partials, grid, st);
 }
 
 extern "C" int gsl_kmeans_assign(const float *data, int64_t N, int D, const float *centroids, int K,

@@ -114,37 +114,70 @@ def _precomputed_map(output_dir, img_name):
 # ----------------------------------------------------------------------------------------
 # the hot path
 # ----------------------------------------------------------------------------------------
+def _stage_maps(seg_maps, shapes, device, label_min, n_classes):
+    """Host int maps -> packed uint8 codes on the device (N2 of SURVEY 8f: label-map staging).
+
+    One process: upload every map (int32), device min/max picks a tight code range, pack.
+    Under torch.distributed every rank holds the same host maps but uploads and packs only its
+    contiguous block of views; the packed blocks (1 byte per pixel) are then broadcast rank by
+    rank over NCCL, so the PCIe cost per rank drops by the world size."""
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    sizes = [h * w for h, w in shapes]
+    starts = np.concatenate(([0], np.cumsum(sizes))).astype(np.int64)
+    total = int(starts[-1])
+    V = len(seg_maps)
+    per, extra = divmod(V, world)
+    cuts = [r * per + min(r, extra) for r in range(world + 1)]
+    v_lo, v_hi = cuts[rank], cuts[rank + 1]
+    mine = int(starts[v_hi] - starts[v_lo])
+    staged = torch.empty(mine, dtype=torch.int32, device=device)
+    off = 0
+    for v in range(v_lo, v_hi):
+        m = seg_maps[v]
+        src = m if isinstance(m, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(m, np.int32))
+        staged[off:off + sizes[v]].copy_(src.reshape(-1), non_blocking=True)
+        off += sizes[v]
+    if label_min is None or n_classes is None:
+        # tight code range from the data (device min/max): fewer histogram rows per Gaussian
+        lo, hi = ops.label_range(staged) if mine else (2**31 - 1, -2**31)
+        if world > 1:
+            mm = torch.tensor([lo, -hi], dtype=torch.int64, device=device)
+            dist.all_reduce(mm, op=dist.ReduceOp.MIN)
+            lo, hi = int(mm[0].item()), -int(mm[1].item())
+        if total == 0:
+            lo, hi = ops.DEFAULT_LABEL_MIN, ops.DEFAULT_LABEL_MIN
+        if hi - lo + 1 > ops.DEFAULT_N_CLASSES:
+            raise ValueError(f"label maps span {hi - lo + 1} values; at most {ops.DEFAULT_N_CLASSES} are supported")
+        label_min, n_classes = lo, hi - lo + 1
+    packed = torch.empty(total, dtype=torch.uint8, device=device)
+    if mine:
+        ops.pack_labels(staged, label_min, n_classes, out=packed[int(starts[v_lo]):int(starts[v_hi])])
+    if world > 1:
+        for r in range(world):
+            lo_px, hi_px = int(starts[cuts[r]]), int(starts[cuts[r + 1]])
+            if hi_px > lo_px:
+                dist.broadcast(packed[lo_px:hi_px], src=r)
+    return packed, label_min, n_classes
+
+
 def lift_labels(positions, cameras, seg_maps, image_sizes=None, device=None, want_near=False,
                 near_eps=1e-4, label_min=None, n_classes=None):
     """Majority-vote labels for `positions` given one segmentation map per camera.
 
-    positions   float32 [N,3] array or device tensor
+    positions   float32 [N,3] array or tensor (under torch.distributed: THIS rank's Gaussians)
     cameras     camera dicts, in voting order
-    seg_maps    list of int arrays [seg_h, seg_w] (NumPy or device tensors), one per camera
+    seg_maps    list of int arrays [seg_h, seg_w] (NumPy or tensors), one per camera
     image_sizes per camera (orig_w, orig_h); default = the map's own size (scale 1.0)
     Returns int32 NumPy labels (and the near-boundary mask when want_near).
     """
     device = torch.device(device if device is not None else "cuda")
     pos = positions if isinstance(positions, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(positions, np.float32))
-    pos = pos.to(device=device, dtype=torch.float32).contiguous()
+    pos = pos.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
     shapes = [tuple(m.shape) for m in seg_maps]
     views = ops.make_views(cameras, shapes, image_sizes)
-    total = int(sum(h * w for h, w in shapes))
-    staged = torch.empty(total, dtype=torch.int32, device=device)
-    off = 0
-    for m, (h, w) in zip(seg_maps, shapes):
-        src = m if isinstance(m, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(m, np.int32))
-        staged[off:off + h * w].copy_(src.reshape(-1), non_blocking=True)
-        off += h * w
-    if label_min is None or n_classes is None:
-        # tight code range from the data (device min/max): fewer histogram rows per Gaussian
-        label_min, n_classes = ops.DEFAULT_LABEL_MIN, 1
-        if total:
-            lo, hi = ops.label_range(staged)
-            if hi - lo + 1 > ops.DEFAULT_N_CLASSES:
-                raise ValueError(f"label maps span {hi - lo + 1} values; at most {ops.DEFAULT_N_CLASSES} are supported")
-            label_min, n_classes = lo, hi - lo + 1
-    packed = ops.pack_labels(staged, label_min, n_classes)
+    packed, label_min, n_classes = _stage_maps(seg_maps, shapes, device, label_min, n_classes)
     res = ops.lift_votes(pos, views, packed, label_min, n_classes, want_near=want_near, near_eps=near_eps)
     if want_near:
         return res[0].cpu().numpy(), res[1].cpu().numpy()

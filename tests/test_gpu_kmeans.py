@@ -91,6 +91,39 @@ def test_step_locked_assignment_and_updates(oracle, n, d, k):
     assert abs(float(shift_fast.item()) - np.linalg.norm(nf - cen)) <= 2e-6 * max(1.0, want_shift)
 
 
+def test_screened_assignment_equals_float64_scan(oracle, monkeypatch):
+    """The float32 screening + float64 near-tie path must return exactly the labels of the plain
+    float64 scan (GSLIFT_KMEANS_EXACT=1) and of the oracle, also on adversarial inputs."""
+    ops = pkg("ops")
+    rng = np.random.default_rng(12)
+    cases = []
+    for d, k in [(6, 10), (59, 64), (16, 5), (33, 40), (3, 200)]:
+        cen = rng.standard_normal((k, d)).astype(np.float32)
+        pts = rng.standard_normal((20000, d)).astype(np.float32)
+        # points on / next to bisecting planes of centroid pairs: near ties in float64
+        i, j = rng.integers(0, k, 4000), rng.integers(0, k, 4000)
+        mid = ((cen[i].astype(np.float64) + cen[j]) / 2).astype(np.float32)
+        wob = mid + (rng.standard_normal(mid.shape) * 1e-6).astype(np.float32)
+        cases.append((f"normal d{d} k{k}", np.concatenate([pts, mid, wob]), cen))
+    cen = (rng.standard_normal((64, 59)) * 0.01 + 1000.0).astype(np.float32)     # far from the origin, tight
+    cases.append(("offset", (rng.standard_normal((30000, 59)) * 0.01 + 1000.0).astype(np.float32), cen))
+    cen = (rng.standard_normal((10, 6)) * 1e-21).astype(np.float32)               # below float32 range when squared
+    cases.append(("tiny", (rng.standard_normal((5000, 6)) * 1e-21).astype(np.float32), cen))
+    cen = (rng.standard_normal((10, 6)) * 1e25).astype(np.float32)                # squares overflow float32
+    cases.append(("huge", (rng.standard_normal((5000, 6)) * 1e25).astype(np.float32), cen))
+    for name, data, cen in cases:
+        want, gap = oracle.kmeans_assign(data, cen, want_gap=True)
+        monkeypatch.delenv("GSLIFT_KMEANS_EXACT", raising=False)
+        fast = ops.kmeans_assign(dev(data), dev(cen)).cpu().numpy()
+        fast2 = ops.kmeans_step(dev(data), dev(cen))[0].cpu().numpy()
+        monkeypatch.setenv("GSLIFT_KMEANS_EXACT", "1")
+        slow = ops.kmeans_assign(dev(data), dev(cen)).cpu().numpy()
+        monkeypatch.delenv("GSLIFT_KMEANS_EXACT", raising=False)
+        assert np.array_equal(fast, slow), f"{name}: screening changed {(fast != slow).sum()} labels"
+        assert np.array_equal(fast, fast2), name
+        assert np.array_equal(fast.astype(np.int64), want), f"{name}: {(fast != want).sum()} differ from the oracle (ties {int((gap == 0).sum())})"
+
+
 def test_ties_duplicates_and_determinism(oracle):
     ops = pkg("ops")
     rng = np.random.default_rng(5)
