@@ -36,4 +36,9 @@ int sm_count();
 // kmeans_ordered.cu: scratch for gsl_kmeans_update_ordered.
 size_t ordered_workspace_bytes(int64_t N, int K);
 
+// kmeans_tc.cu: tensor-core screened assignment (K <= 64, 8 <= D <= 64).
+bool tc_supported(int D, int K);
+int launch_step_tc(bool accumulate, const float *data, int64_t N, int D, const float *centroids, int K,
+                   int32_t *labels, double *partials, int grid, cudaStream_t st);
+
 }  // namespace gsl

@@ -20,6 +20,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "kmeans_common.cuh"
 
 namespace gsl {
 
@@ -42,28 +43,8 @@ static inline StepSmem step_layout(int D, int K, bool accumulate, int dreg)
     s.acc = o;  o += accumulate ? align_up((size_t)K * (D + 1) * sizeof(double), 16) : 0;
     s.cent = o; o += align_up((size_t)K * s.cpitch * sizeof(float), 16);
     s.tile = o; o += align_up((size_t)kStepThreads * s.pitch * sizeof(float), 16);
-    s.lab = o;  o += (size_t)kStepThreads * sizeof(int);
+    s.lab = o;  o += accumulate ? (size_t)K * kStepWarps * sizeof(unsigned) : 0;   // member bits [K][warps]
     s.total = o;
-    return s;
-}
-
-// scipy ckdtree sqeuclidean_distance_double on float64 copies of float32 values.
-__device__ __forceinline__ double sqdist_scipy(const float *__restrict__ c, const float *__restrict__ x, int D)
-{
-    double a0 = 0., a1 = 0., a2 = 0., a3 = 0.;
-    int i = 0;
-    for (; i + 4 <= D; i += 4) {
-        const double d0 = (double)c[i] - (double)x[i];
-        const double d1 = (double)c[i + 1] - (double)x[i + 1];
-        const double d2 = (double)c[i + 2] - (double)x[i + 2];
-        const double d3 = (double)c[i + 3] - (double)x[i + 3];
-        a0 += d0 * d0; a1 += d1 * d1; a2 += d2 * d2; a3 += d3 * d3;
-    }
-    double s = a0 + a1 + a2 + a3;
-    for (; i < D; ++i) {
-        const double d = (double)c[i] - (double)x[i];
-        s += d * d;
-    }
     return s;
 }
 
@@ -128,7 +109,7 @@ kmeans_step_kernel(const float *__restrict__ data, int64_t N, int D, const float
     double *acc = reinterpret_cast<double *>(smem + L.acc);
     float *tile = reinterpret_cast<float *>(smem + L.tile);
     float *cent = reinterpret_cast<float *>(smem + L.cent);
-    int *lab = reinterpret_cast<int *>(smem + L.lab);
+    unsigned *bits = reinterpret_cast<unsigned *>(smem + L.lab);
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int pitch = L.pitch, cpitch = L.cpitch;
 
@@ -144,28 +125,8 @@ kmeans_step_kernel(const float *__restrict__ data, int64_t N, int D, const float
         const int64_t row0 = tl * kStepThreads;
         const int rows = (int)min((int64_t)kStepThreads, N - row0);
         __syncthreads();   // previous tile fully consumed (and cent/acc initialised)
-        // ---- stage the contiguous [rows x D] block, repitched to `pitch` floats per row
-        const float *src = data + row0 * D;
-        const int n_el = rows * D;
-        if (vec_ok && rows == kStepThreads) {
-            const float4 *src4 = reinterpret_cast<const float4 *>(src);
-            for (int i = t; i < (n_el >> 2); i += kStepThreads) {
-                const float4 v = __ldcs(src4 + i);
-                const int e = i << 2;
-                int r = e / D, d = e - r * D;
-                const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    tile[r * pitch + d] = vv[j];
-                    if (++d == D) { d = 0; ++r; }
-                }
-            }
-        } else {
-            for (int i = t; i < n_el; i += kStepThreads) {
-                const int r = i / D, d = i - r * D;
-                tile[r * pitch + d] = __ldcs(src + i);
-            }
-        }
+        stage_tile(tile, pitch, data + row0 * D, rows, D, vec_ok && rows == kStepThreads, t, kStepThreads);
+        if (kAccumulate) zero_member_bits(bits, K, kStepWarps, t, kStepThreads);
         __syncthreads();
         // ---- assignment: thread = row
         int mine = -1;
@@ -184,28 +145,9 @@ kmeans_step_kernel(const float *__restrict__ data, int64_t N, int D, const float
             labels[row0 + t] = mine;
         }
         if (!kAccumulate) continue;
-        lab[t] = mine;
+        tile_member_bits(bits, mine, kStepWarps, lane, warp);
         __syncthreads();
-        // ---- segmented reduction: warp owns clusters k = warp, warp + W, ...
-        for (int k = warp; k < K; k += kStepWarps) {
-            int cnt = 0;
-            for (int d0 = 0; d0 < D; d0 += 32) {
-                const int d = d0 + lane;
-                double s = 0.0;
-                cnt = 0;
-                for (int r0 = 0; r0 < kStepThreads; r0 += 32) {
-                    unsigned m = __ballot_sync(0xffffffffu, lab[r0 + lane] == k);
-                    cnt += __popc(m);
-                    while (m) {
-                        const int r = r0 + __ffs(m) - 1;
-                        m &= m - 1;
-                        if (d < D) s += (double)tile[r * pitch + d];
-                    }
-                }
-                if (d < D && cnt) acc[k * (D + 1) + d] += s;
-            }
-            if (lane == 0 && cnt) acc[k * (D + 1) + D] += (double)cnt;
-        }
+        accumulate_tile(acc, tile, pitch, bits, K, D, lane, warp, kStepWarps);
     }
     if (kAccumulate) {
         __syncthreads();
@@ -314,10 +256,19 @@ static int launch_step_t(const float *data, int64_t N, int D, const float *centr
     return GSL_OK;
 }
 
+// GSLIFT_KMEANS_TC=0 keeps the float32 CUDA-core screening even where tensor cores apply.
+static bool allow_tc()
+{
+    const char *e = getenv("GSLIFT_KMEANS_TC");
+    return !(e && e[0] == '0');
+}
+
 template <bool kAcc>
 static int launch_step(const float *data, int64_t N, int D, const float *centroids, int K,
                        int32_t *labels, double *partials, int grid, cudaStream_t st)
 {
+    if (!force_exact() && allow_tc() && K >= 16 && tc_supported(D, K))
+        return launch_step_tc(kAcc, data, N, D, centroids, K, labels, partials, grid, st);
     // the screened kernel pads the centroid block to DREG floats per row: fall back to the
     // float64 scan when that does not fit or the row does not fit the register block
     if (!force_exact() && D <= 64) {

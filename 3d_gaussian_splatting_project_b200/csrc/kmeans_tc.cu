@@ -1,0 +1,362 @@
+// K-means assignment with tensor-core screening (K <= 64, 8 <= D <= 64), sm_100a.
+//
+// The labels must be exactly those of scipy's float64 scan (3D_clustering/k_means.py:116-122);
+// what can be approximate is the WORK that proves most centroids cannot win.  Three stages per
+// 256-row tile, every stage with a rigorous error bound so that the set it forwards always
+// contains the true nearest centroid (and every exact tie):
+//
+//   A  tensor cores: with m = mean of the centroids, x' = x - m, c' = c - m (distances are
+//      translation invariant), rank k by  g_k = |c'_k|^2 - 2 x'.c'_k  where the dot products of
+//      a 32-row x 64-centroid block are TF32 mma.sync.m16n8k8 (operands rounded with
+//      cvt.rna.tf32, FP32 accumulate).  |g_k - exact| <= E_k = 1.5 * 2^-9 |x'| |c'_k| +
+//      2^-22 (|x'| + |c'_k|)^2 (operand rounding 2^-11 each, doubled by the factor 2, 1.5x margin
+//      for the accumulation; second term: rounding of the centring itself).  Candidates =
+//      { k : g_k - E_k <= min_j (g_j + E_j) }.  Typically one or two per row.
+//   B  CUDA cores, candidates only: float32 sum of (x-c)^2 on the original values, relative
+//      error (D + 3) 2^-24; decided when the two smallest differ by more than that.
+//   C  float64, near ties only: scipy-order distance, lowest index first.
+//
+// gsl_kmeans_screen_selftest measures stage A's bound on real data: for every (row, k) it
+// compares (g_k - g_0) with the float64 (d2_k - d2_0) and counts violations of E_k + E_0.
+//
+// The per-cluster float64 sums that follow are the shared segmented reduction
+// (kmeans_common.cuh).  Compiled with -fmad=false.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "kmeans_common.cuh"
+
+namespace gsl {
+
+constexpr int kTcThreads = 256;          // 8 warps x 32 rows
+constexpr int kTcRows = 256;
+constexpr int kTcKP = 64;                // centroids padded to 64 (8 n-tiles)
+constexpr int kTcCPitch = 68;            // c' row pitch: 68 % 32 == 4 -> conflict-free B fragments
+
+struct TcSmem {
+    size_t acc, cprime, cn2, nc, mean, tile, lab, mask, total;
+    int pitch;     // tile row pitch, pitch % 8 == 4 -> conflict-free A fragments
+    int ksteps;    // ceil(D / 8)
+};
+
+static inline TcSmem tc_layout(int D, int K, bool accumulate)
+{
+    TcSmem s;
+    s.ksteps = (D + 7) / 8;
+    int p = (D + 3) / 4 * 4;
+    if (p % 8 != 4) p += 4;
+    s.pitch = p;
+    size_t o = 0;
+    s.acc = o;    o += accumulate ? align_up((size_t)K * (D + 1) * sizeof(double), 16) : 0;
+    s.cprime = o; o += (size_t)kTcKP * kTcCPitch * sizeof(float);
+    s.cn2 = o;    o += kTcKP * sizeof(float);
+    s.nc = o;     o += kTcKP * sizeof(float);
+    s.mean = o;   o += 64 * sizeof(float);
+    s.tile = o;   o += align_up((size_t)kTcRows * s.pitch * sizeof(float) + 64, 16);   // + slack past the last row
+    s.lab = o;    o += accumulate ? (size_t)K * (kTcThreads / 32) * sizeof(unsigned) : 0;   // member bits [K][warps]
+    s.mask = o;   o += kTcRows * sizeof(unsigned long long);
+    s.total = o;
+    return s;
+}
+
+__device__ __forceinline__ uint32_t to_tf32(float x)
+{
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// Stage A for the 32 rows of one warp.  On return, for mt in {0,1}, h in {0,1}: row
+// mt*16 + (lane>>2) + 8h has, in this thread, g[mt][j][2h+c] and E[...] for centroid
+// 8j + 2(lane&3) + c, and nx[mt][h] = |x'| (upper bound).
+struct ScreenOut {
+    float g[2][8][4];
+    float nx[2][2];
+};
+
+__device__ __forceinline__ void screen_warp(ScreenOut &o, const float *__restrict__ xt, int pitch, int D, int ksteps,
+                                            const float *__restrict__ cprime, const float *__restrict__ cn2,
+                                            const float *__restrict__ mean, int lane)
+{
+    const int g = lane >> 2, t = lane & 3;
+    float nx2[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) o.g[mt][j][c] = 0.f;
+
+    for (int ks = 0; ks < ksteps; ++ks) {
+        const int d0 = 8 * ks + t, d1 = d0 + 4;
+        const bool in0 = d0 < D, in1 = d1 < D;
+        const float m0 = mean[d0], m1 = mean[d1];
+        uint32_t a[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            const float *r0 = xt + (mt * 16 + g) * pitch, *r1 = r0 + 8 * pitch;
+            const float x00 = in0 ? r0[d0] - m0 : 0.f, x10 = in0 ? r1[d0] - m0 : 0.f;
+            const float x01 = in1 ? r0[d1] - m1 : 0.f, x11 = in1 ? r1[d1] - m1 : 0.f;
+            nx2[mt][0] = fmaf(x00, x00, fmaf(x01, x01, nx2[mt][0]));
+            nx2[mt][1] = fmaf(x10, x10, fmaf(x11, x11, nx2[mt][1]));
+            a[mt][0] = to_tf32(x00); a[mt][1] = to_tf32(x10); a[mt][2] = to_tf32(x01); a[mt][3] = to_tf32(x11);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float *cp = cprime + (8 * j + g) * kTcCPitch + 8 * ks + t;
+            const uint32_t b0 = __float_as_uint(cp[0]), b1 = __float_as_uint(cp[4]);
+            mma_tf32(o.g[0][j], a[0], b0, b1);
+            mma_tf32(o.g[1][j], a[1], b0, b1);
+        }
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float v = nx2[mt][h];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            o.nx[mt][h] = sqrtf(v) * 1.0001f;
+        }
+    // dot -> g = |c'|^2 - 2 x'.c'
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) o.g[mt][j][c] = cn2[8 * j + 2 * t + (c & 1)] - 2.f * o.g[mt][j][c];
+}
+
+__device__ __forceinline__ float screen_bound(float nx, float nck)
+{
+    const float s = nx + nck;
+    return 2.9296875e-3f * nx * nck + 2.384185791015625e-7f * s * s;     // 1.5 * 2^-9, 2^-22
+}
+
+// Stages B and C for one row: candidates given as a bit mask over k.
+__device__ __forceinline__ int refine_row(unsigned long long mask, const float *__restrict__ x,
+                                          const float *__restrict__ centroids, int D, float eps)
+{
+    if (__popcll(mask) == 1) return __ffsll((long long)mask) - 1;
+    float s1 = INFINITY, s2 = INFINITY;
+    int k1 = 0;
+    for (unsigned long long m = mask; m; m &= m - 1) {
+        const int k = __ffsll((long long)m) - 1;
+        const float *c = centroids + (size_t)k * D;
+        float s = 0.f;
+        for (int d = 0; d < D; ++d) {
+            const float df = x[d] - __ldg(c + d);
+            s = fmaf(df, df, s);
+        }
+        if (s < s1) { s2 = s1; s1 = s; k1 = k; }
+        else if (s < s2) s2 = s;
+    }
+    if ((s2 * (1.f - eps) > s1 * (1.f + eps)) && (s1 > 1e-30f)) return k1;
+    const float bound = s1 * (1.f + 2.f * eps);
+    double best = INFINITY;
+    int mine = 0;                                    // the float64 scan starts from (inf, 0) and needs d2 < best
+    for (unsigned long long m = mask; m; m &= m - 1) {
+        const int k = __ffsll((long long)m) - 1;
+        const float *c = centroids + (size_t)k * D;
+        float s = 0.f;
+        for (int d = 0; d < D; ++d) {
+            const float df = x[d] - __ldg(c + d);
+            s = fmaf(df, df, s);
+        }
+        if (!(s * (1.f - 2.f * eps) <= bound) && (s1 > 1e-30f)) continue;
+        const double d2 = sqdist_scipy(c, x, D);
+        if (d2 < best) { best = d2; mine = k; }
+    }
+    return mine;
+}
+
+template <bool kAccumulate, bool kCheck>
+__global__ void __launch_bounds__(kTcThreads, 2)
+kmeans_step_tc_kernel(const float *__restrict__ data, int64_t N, int D, const float *__restrict__ centroids,
+                      int K, int32_t *__restrict__ labels, double *__restrict__ partials,
+                      TcSmem L, int vec_ok, float eps, unsigned long long *__restrict__ check_out)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    double *acc = reinterpret_cast<double *>(smem + L.acc);
+    float *cprime = reinterpret_cast<float *>(smem + L.cprime);
+    float *cn2 = reinterpret_cast<float *>(smem + L.cn2);
+    float *nc = reinterpret_cast<float *>(smem + L.nc);
+    float *mean = reinterpret_cast<float *>(smem + L.mean);
+    float *tile = reinterpret_cast<float *>(smem + L.tile);
+    unsigned *bits = reinterpret_cast<unsigned *>(smem + L.lab);
+    unsigned long long *maskbuf = reinterpret_cast<unsigned long long *>(smem + L.mask);
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int pitch = L.pitch;
+
+    // ---- per-CTA prologue: centre the centroids, round to TF32, norms
+    if (t < 64) {
+        float s = 0.f;
+        if (t < D)
+            for (int k = 0; k < K; ++k) s += centroids[k * D + t];
+        mean[t] = t < D ? s / (float)K : 0.f;
+    }
+    __syncthreads();
+    for (int i = t; i < kTcKP * kTcCPitch; i += kTcThreads) {
+        const int k = i / kTcCPitch, d = i - k * kTcCPitch;
+        const float v = (k < K && d < D) ? centroids[k * D + d] - mean[d] : 0.f;
+        cprime[i] = v;                                  // float32 for now; rounded to TF32 below
+    }
+    __syncthreads();
+    if (t < kTcKP) {
+        float s = 0.f;
+        for (int d = 0; d < D; ++d) s = fmaf(cprime[t * kTcCPitch + d], cprime[t * kTcCPitch + d], s);
+        cn2[t] = t < K ? s : INFINITY;                  // padded centroids can never be candidates
+        nc[t] = t < K ? sqrtf(s) * 1.0001f : 0.f;
+    }
+    __syncthreads();
+    for (int i = t; i < kTcKP * kTcCPitch; i += kTcThreads) cprime[i] = __uint_as_float(to_tf32(cprime[i]));
+    if (kAccumulate)
+        for (int i = t; i < K * (D + 1); i += kTcThreads) acc[i] = 0.0;
+    for (int i = t; i < 16; i += kTcThreads) tile[kTcRows * pitch + i] = 0.f;   // slack read by the last row's padding
+    const unsigned long long kmask = K >= 64 ? ~0ull : ((1ull << K) - 1ull);
+    unsigned long long n_viol = 0, n_cand = 0;
+
+    const int64_t n_tiles = (N + kTcRows - 1) / kTcRows;
+    for (int64_t tl = blockIdx.x; tl < n_tiles; tl += gridDim.x) {
+        const int64_t row0 = tl * kTcRows;
+        const int rows = (int)min((int64_t)kTcRows, N - row0);
+        __syncthreads();
+        stage_tile(tile, pitch, data + row0 * D, rows, D, vec_ok && rows == kTcRows, t, kTcThreads);
+        if (rows < kTcRows)                              // rows past the end: finite zeros
+            for (int i = rows * pitch + t; i < kTcRows * pitch; i += kTcThreads) tile[i] = 0.f;
+        if (kAccumulate) zero_member_bits(bits, K, kTcThreads / 32, t, kTcThreads);
+        __syncthreads();
+
+        // ---- stage A: this warp's 32 rows against all centroids
+        ScreenOut so;
+        screen_warp(so, tile + warp * 32 * pitch, pitch, D, L.ksteps, cprime, cn2, mean, lane);
+        const int g = lane >> 2, tq = lane & 3;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const float nx = so.nx[mt][h];
+                float up = INFINITY;
+                float lo[16];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const int n = 8 * j + 2 * tq + c;
+                        const float gk = so.g[mt][j][2 * h + c];
+                        const float e = screen_bound(nx, nc[n]);
+                        up = fminf(up, gk + e);
+                        lo[2 * j + c] = gk - e;
+                    }
+                up = fminf(up, __shfl_xor_sync(0xffffffffu, up, 1));
+                up = fminf(up, __shfl_xor_sync(0xffffffffu, up, 2));
+                unsigned m_lo = 0, m_hi = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const int n = 8 * j + 2 * tq + c;
+                        const unsigned bit = (lo[2 * j + c] <= up) ? 1u : 0u;
+                        if (n < 32) m_lo |= bit << n; else m_hi |= bit << (n - 32);
+                    }
+                m_lo |= __shfl_xor_sync(0xffffffffu, m_lo, 1); m_hi |= __shfl_xor_sync(0xffffffffu, m_hi, 1);
+                m_lo |= __shfl_xor_sync(0xffffffffu, m_lo, 2); m_hi |= __shfl_xor_sync(0xffffffffu, m_hi, 2);
+                unsigned long long mask = (((unsigned long long)m_hi << 32) | m_lo) & kmask;
+                if (mask == 0 || !(nx < INFINITY)) mask = kmask;   // NaN/Inf/overflowing rows: everything is a candidate
+                if (tq == 0) maskbuf[warp * 32 + mt * 16 + g + 8 * h] = mask;
+
+                if (kCheck) {
+                    // bound check: (g_k - g_0) vs float64 (d2_k - d2_0), tolerance E_k + E_0
+                    const int r = warp * 32 + mt * 16 + g + 8 * h;
+                    const float g0 = __shfl_sync(0xffffffffu, so.g[mt][0][2 * h], lane & ~3);
+                    const float e0 = screen_bound(nx, nc[0]);
+                    if (r < rows) {
+                        const float *x = tile + r * pitch;
+                        const double d0 = sqdist_scipy(centroids, x, D);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+#pragma unroll
+                            for (int c = 0; c < 2; ++c) {
+                                const int n = 8 * j + 2 * tq + c;
+                                if (n >= K) continue;
+                                const double dk = sqdist_scipy(centroids + (size_t)n * D, x, D);
+                                const double err = fabs(((double)so.g[mt][j][2 * h + c] - (double)g0) - (dk - d0));
+                                const double tol = (double)screen_bound(nx, nc[n]) + (double)e0;
+                                if (!(err <= tol)) ++n_viol;
+                            }
+                    }
+                }
+            }
+        __syncwarp();
+
+        // ---- stages B, C: lane = row
+        int mine = -1;
+        if (t < rows) {
+            const unsigned long long mask = maskbuf[t];
+            if (kCheck) n_cand += __popcll(mask);
+            mine = refine_row(mask, tile + t * pitch, centroids, D, eps);
+            labels[row0 + t] = mine;
+        }
+        if (!kAccumulate) continue;
+        tile_member_bits(bits, mine, kTcThreads / 32, lane, warp);
+        __syncthreads();
+        accumulate_tile(acc, tile, pitch, bits, K, D, lane, warp, kTcThreads / 32);
+    }
+    if (kAccumulate) {
+        __syncthreads();
+        double *out = partials + (size_t)blockIdx.x * K * (D + 1);
+        for (int i = t; i < K * (D + 1); i += kTcThreads) out[i] = acc[i];
+    }
+    if (kCheck) {
+        atomicAdd(check_out, n_viol);
+        atomicAdd(check_out + 1, n_cand);
+    }
+}
+
+bool tc_supported(int D, int K)
+{
+    return K >= 1 && K <= 64 && D >= 8 && D <= 64;
+}
+
+template <bool kAcc, bool kCheck>
+static int launch_tc_t(const float *data, int64_t N, int D, const float *centroids, int K, int32_t *labels,
+                       double *partials, int grid, unsigned long long *check_out, cudaStream_t st)
+{
+    const TcSmem L = tc_layout(D, K, kAcc);
+    if (L.total > 227 * 1024) return fail(GSL_EINVAL, "kmeans (tensor-core screening): %zu B of shared memory", L.total);
+    GSL_CUDA_TRY(cudaFuncSetAttribute(kmeans_step_tc_kernel<kAcc, kCheck>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    const int vec_ok = (((uintptr_t)data & 15) == 0) && (((size_t)kTcRows * D) % 4 == 0);
+    const float eps = (float)((D + 12) * 5.9604644775390625e-08);
+    kmeans_step_tc_kernel<kAcc, kCheck><<<grid, kTcThreads, L.total, st>>>(data, N, D, centroids, K, labels, partials, L, vec_ok, eps, check_out);
+    GSL_LAUNCH_CHECK("kmeans_step_tc_kernel");
+    return GSL_OK;
+}
+
+int launch_step_tc(bool accumulate, const float *data, int64_t N, int D, const float *centroids, int K,
+                   int32_t *labels, double *partials, int grid, cudaStream_t st)
+{
+    return accumulate ? launch_tc_t<true, false>(data, N, D, centroids, K, labels, partials, grid, nullptr, st)
+                      : launch_tc_t<false, false>(data, N, D, centroids, K, labels, partials, grid, nullptr, st);
+}
+
+}  // namespace gsl
+
+using namespace gsl;
+
+extern "C" int gsl_kmeans_screen_selftest(const float *data, int64_t N, int D, const float *centroids, int K,
+                                          int32_t *labels, unsigned long long *out2, void *stream)
+{
+    if (!data || !centroids || !labels || !out2 || N < 0) return fail(GSL_EINVAL, "gsl_kmeans_screen_selftest: bad argument");
+    if (!tc_supported(D, K)) return fail(GSL_EINVAL, "gsl_kmeans_screen_selftest: needs K <= 64 and 8 <= D <= 64");
+    if (N == 0) return GSL_OK;
+    const int64_t tiles = (N + kTcRows - 1) / kTcRows;
+    const int64_t cap = (int64_t)sm_count() * 2;
+    return launch_tc_t<false, true>(data, N, D, centroids, K, labels, nullptr, (int)(tiles < cap ? tiles : cap), out2, (cudaStream_t)stream);
+}

@@ -165,6 +165,16 @@ int gsl_kmeans_update_ordered(const float *data, const int32_t *labels, int64_t 
                               const float *old_centroids, float *new_centroids, float *shift,
                               void *ws, size_t ws_bytes, void *stream);
 
+/*
+ * Test hook for the tensor-core screening of gsl_kmeans_assign/step (K <= 64, 8 <= D <= 64):
+ * runs the assignment and, for every (row, centroid), compares the screened ranking value with
+ * the float64 distance.  out2[0] += number of (row, centroid) pairs whose error exceeds the
+ * bound the kernel relies on (must stay 0); out2[1] += total candidates forwarded to the
+ * float32/float64 stages.  out2 is a device array the caller zeroes.
+ */
+int gsl_kmeans_screen_selftest(const float *data, int64_t N, int D, const float *centroids, int K,
+                               int32_t *labels, unsigned long long *out2, void *stream);
+
 /* Recolouring (km:99-101, :147-149): colors[i][0..3) = palette[labels[i] % 8]; `palette` is a
  * device float32 [8][3] the host fills with COLORS (km:8), divided by 255.0 or not. */
 int gsl_recolor(const int32_t *labels, int64_t N, const float *palette, float *colors, void *stream);

@@ -111,10 +111,20 @@ def test_screened_assignment_equals_float64_scan(oracle, monkeypatch):
     cases.append(("tiny", (rng.standard_normal((5000, 6)) * 1e-21).astype(np.float32), cen))
     cen = (rng.standard_normal((10, 6)) * 1e25).astype(np.float32)                # squares overflow float32
     cases.append(("huge", (rng.standard_normal((5000, 6)) * 1e25).astype(np.float32), cen))
+    cen = (rng.standard_normal((64, 59)) * 0.01 + 1000.0).astype(np.float32)
+    pts = rng.standard_normal((30000, 59)).astype(np.float32) * 0.01 + 1000.0
+    pts[::3] = np.nan                                                              # NaN rows -> label 0 like the scan
+    pts[1::7, 5] = np.inf
+    cases.append(("nonfinite", pts.astype(np.float32), cen))
     for name, data, cen in cases:
-        want, gap = oracle.kmeans_assign(data, cen, want_gap=True)
+        with np.errstate(all="ignore"):
+            want, gap = oracle.kmeans_assign(data, cen, want_gap=True)
         monkeypatch.delenv("GSLIFT_KMEANS_EXACT", raising=False)
+        monkeypatch.setenv("GSLIFT_KMEANS_TC", "0")                                # float32 CUDA-core screening
+        cc = ops.kmeans_assign(dev(data), dev(cen)).cpu().numpy()
+        monkeypatch.delenv("GSLIFT_KMEANS_TC", raising=False)                      # tensor-core screening where it applies
         fast = ops.kmeans_assign(dev(data), dev(cen)).cpu().numpy()
+        assert np.array_equal(fast, cc), f"{name}: tensor-core and CUDA-core screening disagree on {(fast != cc).sum()} rows"
         fast2 = ops.kmeans_step(dev(data), dev(cen))[0].cpu().numpy()
         monkeypatch.setenv("GSLIFT_KMEANS_EXACT", "1")
         slow = ops.kmeans_assign(dev(data), dev(cen)).cpu().numpy()
@@ -122,6 +132,34 @@ def test_screened_assignment_equals_float64_scan(oracle, monkeypatch):
         assert np.array_equal(fast, slow), f"{name}: screening changed {(fast != slow).sum()} labels"
         assert np.array_equal(fast, fast2), name
         assert np.array_equal(fast.astype(np.int64), want), f"{name}: {(fast != want).sum()} differ from the oracle (ties {int((gap == 0).sum())})"
+
+
+def test_tensor_core_screening_bound_holds_on_data():
+    """Stage A forwards a candidate set that provably contains the nearest centroid only if its
+    error bound holds; the self-test kernel measures the bound against float64 on every
+    (row, centroid) pair and reports how many candidates survive."""
+    native, scene = pkg("_native"), pkg("scene")
+    rng = np.random.default_rng(3)
+    sets = []
+    data = scene.blob_features(200_000, 59, n_blobs=64, seed=5)
+    sets.append(("C5 first iteration (centroids = data rows)", data, data[rng.choice(len(data), 64, replace=False)]))
+    lab = np.argmin(((data[:, None, :3] - data[rng.choice(len(data), 64), None, :3][:, 0][None]) ** 2).sum(-1), 1)
+    cen = np.stack([data[lab == k].mean(0) if (lab == k).any() else data[k] for k in range(64)]).astype(np.float32)
+    sets.append(("C5 converged-like (centroids = blob means)", data, cen))
+    off = (rng.standard_normal((100_000, 32)) * 0.05 + 500.0).astype(np.float32)
+    sets.append(("far offset, tight", off, off[rng.choice(len(off), 40, replace=False)]))
+    wide = (rng.standard_normal((100_000, 8)) * np.array([1e-3, 1, 1e3, 1, 1, 1e2, 1, 1e-2])).astype(np.float32)
+    sets.append(("mixed scales D=8", wide, wide[rng.choice(len(wide), 16, replace=False)]))
+    for name, x, c in sets:
+        out = torch.zeros(2, dtype=torch.int64, device=DEV)
+        labels = torch.empty(len(x), dtype=torch.int32, device=DEV)
+        dx, dc = dev(x), dev(c)
+        native.check(native.lib().gsl_kmeans_screen_selftest(dx.data_ptr(), len(x), x.shape[1], dc.data_ptr(), len(c),
+                                                             labels.data_ptr(), out.data_ptr(), None))
+        torch.cuda.synchronize()
+        viol, cand = (int(v) for v in out.tolist())
+        print(f"[tc screen] {name}: bound violations {viol}, candidates per row {cand / len(x):.3f}")
+        assert viol == 0
 
 
 def test_ties_duplicates_and_determinism(oracle):
