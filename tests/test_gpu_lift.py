@@ -120,6 +120,31 @@ def test_shared_reciprocal_division_is_ieee_exact():
         assert int(bad.item()) == 0, f"{int(bad.item())} of {n} quotients differ from IEEE division ({kind})"
 
 
+def test_ordering_and_culling_do_not_change_results(oracle, monkeypatch):
+    """Spatial ordering + per-tile frustum culling (GSLIFT_LIFT_ORDER, default on) is an
+    execution-order change only: same labels and same near-boundary set as the plain sweep,
+    also when most pairs are invisible (bundled cameras) and with non-finite positions."""
+    c = load_lift_case("lift_bundled_halfres")
+    rng = np.random.default_rng(4)
+    pos = (rng.standard_normal((150_000, 3)) * 2.0).astype(np.float32)
+    pos[::5000] = np.nan
+    pos[7::9000, 1] = np.inf
+    maps = [c["maps"][i % len(c["maps"])] for i in range(len(c["cameras"]))]
+    with np.errstate(all="ignore"):
+        want, near, vis = oracle.lift_votes(pos, oracle.make_views(c["cameras"], c["shapes"], c["sizes"]), c["flat"],
+                                            eps=1e-4, want_near=True)
+    out = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("GSLIFT_LIFT_ORDER", flag)
+        lab, nr = gpu_lift(pos, c["cameras"], maps, c["sizes"], want_near=True, near_eps=1e-4)
+        out[flag] = (lab.cpu().numpy(), nr.cpu().numpy())
+    monkeypatch.delenv("GSLIFT_LIFT_ORDER", raising=False)
+    assert np.array_equal(out["1"][0], out["0"][0]) and np.array_equal(out["1"][1], out["0"][1])
+    compare(out["1"][0], want)
+    assert np.array_equal(out["1"][1], near)
+    print(f"[order/cull] bundled cameras: {vis / (len(pos) * len(c['cameras'])):.1%} of pairs visible")
+
+
 def test_view_window_and_chunking_do_not_change_results(oracle):
     cams, pos, maps = _scene(5000, 11, 160, 90, seed=7)
     base = gpu_lift(pos, cams, list(maps), None).cpu().numpy()
