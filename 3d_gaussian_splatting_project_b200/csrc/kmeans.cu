@@ -43,7 +43,7 @@ static inline StepSmem step_layout(int D, int K, bool accumulate, int dreg)
     s.acc = o;  o += accumulate ? align_up((size_t)K * (D + 1) * sizeof(double), 16) : 0;
     s.cent = o; o += align_up((size_t)K * s.cpitch * sizeof(float), 16);
     s.tile = o; o += align_up((size_t)kStepThreads * s.pitch * sizeof(float), 16);
-    s.lab = o;  o += accumulate ? (size_t)K * kStepWarps * sizeof(unsigned) : 0;   // member bits [K][warps]
+    s.lab = o;  o += accumulate ? align_up((size_t)K * kStepWarps * sizeof(unsigned) + (size_t)(K + 2) * 2 + (size_t)kStepThreads * 2, 16) : 0;   // member bits [K][warps], cstart[K+1], order[rows]
     s.total = o;
     return s;
 }
@@ -110,6 +110,8 @@ kmeans_step_kernel(const float *__restrict__ data, int64_t N, int D, const float
     float *tile = reinterpret_cast<float *>(smem + L.tile);
     float *cent = reinterpret_cast<float *>(smem + L.cent);
     unsigned *bits = reinterpret_cast<unsigned *>(smem + L.lab);
+    unsigned short *cstart = reinterpret_cast<unsigned short *>(bits + K * kStepWarps);
+    unsigned short *order = cstart + ((K + 2) & ~1);
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int pitch = L.pitch, cpitch = L.cpitch;
 
@@ -145,9 +147,13 @@ kmeans_step_kernel(const float *__restrict__ data, int64_t N, int D, const float
             labels[row0 + t] = mine;
         }
         if (!kAccumulate) continue;
-        tile_member_bits(bits, mine, kStepWarps, lane, warp);
+        const unsigned same = tile_member_bits(bits, mine, kStepWarps, lane, warp);
         __syncthreads();
-        accumulate_tile(acc, tile, pitch, bits, K, D, lane, warp, kStepWarps);
+        if (warp == 0) tile_cluster_starts(bits, cstart, K, kStepWarps, lane);
+        __syncthreads();
+        tile_row_order(bits, cstart, order, mine, same, kStepWarps, t, lane, warp);
+        __syncthreads();
+        accumulate_tile(acc, tile, pitch, cstart, order, K, D, lane, warp, kStepWarps);
     }
     if (kAccumulate) {
         __syncthreads();

@@ -34,8 +34,8 @@ constexpr int kTcKP = 64;                // centroids padded to 64 (8 n-tiles)
 constexpr int kTcCPitch = 68;            // c' row pitch: 68 % 32 == 4 -> conflict-free B fragments
 
 struct TcSmem {
-    size_t acc, cprime, cn2, nc, mean, tile, lab, mask, total;
-    int pitch;     // tile row pitch, pitch % 8 == 4 -> conflict-free A fragments
+    size_t acc, cprime, cn2, nc, mean, tile, lab, mask, bar, total;
+    int pitch;     // tile row pitch in floats (= D: the global block is copied verbatim)
     int ksteps;    // ceil(D / 8)
 };
 
@@ -43,18 +43,17 @@ static inline TcSmem tc_layout(int D, int K, bool accumulate)
 {
     TcSmem s;
     s.ksteps = (D + 7) / 8;
-    int p = (D + 3) / 4 * 4;
-    if (p % 8 != 4) p += 4;
-    s.pitch = p;
+    s.pitch = D;        // rows stay packed: the tile is one contiguous bulk copy of the [256][D] block
     size_t o = 0;
     s.acc = o;    o += accumulate ? align_up((size_t)K * (D + 1) * sizeof(double), 16) : 0;
     s.cprime = o; o += (size_t)kTcKP * kTcCPitch * sizeof(float);
     s.cn2 = o;    o += kTcKP * sizeof(float);
-    s.nc = o;     o += kTcKP * sizeof(float);
+    s.nc = o;     o += 2 * kTcKP * sizeof(float);
     s.mean = o;   o += 64 * sizeof(float);
     s.tile = o;   o += align_up((size_t)kTcRows * s.pitch * sizeof(float) + 64, 16);   // + slack past the last row
-    s.lab = o;    o += accumulate ? (size_t)K * (kTcThreads / 32) * sizeof(unsigned) : 0;   // member bits [K][warps]
+    s.lab = o;    o += accumulate ? align_up((size_t)K * (kTcThreads / 32) * sizeof(unsigned) + (size_t)(K + 2) * 2 + (size_t)kTcRows * 2, 16) : 0;   // member bits [K][warps], cstart[K+1], order[rows]
     s.mask = o;   o += kTcRows * sizeof(unsigned long long);
+    s.bar = o;    o += 16;                                   // mbarrier of the bulk copy
     s.total = o;
     return s;
 }
@@ -71,6 +70,38 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// ---- TMA 1-D bulk copy of a whole tile (global -> shared), completion on an mbarrier ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(void *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+// One thread: order prior generic-proxy accesses to the buffer before the async-proxy write,
+// arm the barrier with the byte count and launch the copy.
+__device__ __forceinline__ void bulk_load_tile(void *dst, const void *src, unsigned bytes, void *bar)
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(void *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
 // Stage A for the 32 rows of one warp.  On return, for mt in {0,1}, h in {0,1}: row
@@ -134,10 +165,12 @@ __device__ __forceinline__ void screen_warp(ScreenOut &o, const float *__restric
             for (int c = 0; c < 4; ++c) o.g[mt][j][c] = cn2[8 * j + 2 * t + (c & 1)] - 2.f * o.g[mt][j][c];
 }
 
-__device__ __forceinline__ float screen_bound(float nx, float nck)
+// E_k = 1.5 * 2^-9 |x'| |c'_k| + 2^-22 (|x'| + |c'_k|)^2, evaluated as an upper bound with
+// (a + b)^2 <= 2 a^2 + 2 b^2:   E_k <= |x'| * ea_k + eb_k + 2^-21 |x'|^2,
+// ea_k = 1.5 * 2^-9 |c'_k| and eb_k = 2^-21 |c'_k|^2 tabulated per centroid.
+__device__ __forceinline__ float screen_bound(float nx, float nx_term, float ea, float eb)
 {
-    const float s = nx + nck;
-    return 2.9296875e-3f * nx * nck + 2.384185791015625e-7f * s * s;     // 1.5 * 2^-9, 2^-22
+    return fmaf(nx, ea, eb) + nx_term;
 }
 
 // Stages B and C for one row: candidates given as a bit mask over k.
@@ -187,11 +220,14 @@ kmeans_step_tc_kernel(const float *__restrict__ data, int64_t N, int D, const fl
     double *acc = reinterpret_cast<double *>(smem + L.acc);
     float *cprime = reinterpret_cast<float *>(smem + L.cprime);
     float *cn2 = reinterpret_cast<float *>(smem + L.cn2);
-    float *nc = reinterpret_cast<float *>(smem + L.nc);
+    float *eab = reinterpret_cast<float *>(smem + L.nc);       // interleaved {ea_k, eb_k}, see screen_bound
     float *mean = reinterpret_cast<float *>(smem + L.mean);
     float *tile = reinterpret_cast<float *>(smem + L.tile);
     unsigned *bits = reinterpret_cast<unsigned *>(smem + L.lab);
+    unsigned short *cstart = reinterpret_cast<unsigned short *>(bits + K * (kTcThreads / 32));
+    unsigned short *order = cstart + ((K + 2) & ~1);
     unsigned long long *maskbuf = reinterpret_cast<unsigned long long *>(smem + L.mask);
+    void *bar = smem + L.bar;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int pitch = L.pitch;
 
@@ -213,24 +249,38 @@ kmeans_step_tc_kernel(const float *__restrict__ data, int64_t N, int D, const fl
         float s = 0.f;
         for (int d = 0; d < D; ++d) s = fmaf(cprime[t * kTcCPitch + d], cprime[t * kTcCPitch + d], s);
         cn2[t] = t < K ? s : INFINITY;                  // padded centroids can never be candidates
-        nc[t] = t < K ? sqrtf(s) * 1.0001f : 0.f;
+        const float ncu = t < K ? sqrtf(s) * 1.0001f : 0.f;
+        eab[2 * t] = 2.9296875e-3f * ncu;               // 1.5 * 2^-9 |c'_k|
+        eab[2 * t + 1] = 4.76837158203125e-7f * ncu * ncu * 1.0001f;   // 2^-21 |c'_k|^2
     }
     __syncthreads();
     for (int i = t; i < kTcKP * kTcCPitch; i += kTcThreads) cprime[i] = __uint_as_float(to_tf32(cprime[i]));
     if (kAccumulate)
         for (int i = t; i < K * (D + 1); i += kTcThreads) acc[i] = 0.0;
-    for (int i = t; i < 16; i += kTcThreads) tile[kTcRows * pitch + i] = 0.f;   // slack read by the last row's padding
     const unsigned long long kmask = K >= 64 ? ~0ull : ((1ull << K) - 1ull);
     unsigned long long n_viol = 0, n_cand = 0;
 
+    // Tiles arrive by TMA bulk copy: full 256-row tiles of a 16-byte aligned matrix are one
+    // cp.async.bulk each (no staging instructions, no registers); the copy of the NEXT tile is
+    // launched as soon as the buffer is free, i.e. right after this tile's accumulation.
     const int64_t n_tiles = (N + kTcRows - 1) / kTcRows;
+    const unsigned tile_bytes = (unsigned)(kTcRows * D * sizeof(float));
+    unsigned phase = 0;
+    if (t == 0) mbar_init(bar, 1);
+    __syncthreads();
+    auto bulk_ok = [&](int64_t tl) { return vec_ok && (tl + 1) * kTcRows <= N; };
+    if (t == 0 && (int64_t)blockIdx.x < n_tiles && bulk_ok(blockIdx.x))
+        bulk_load_tile(tile, data + (int64_t)blockIdx.x * kTcRows * D, tile_bytes, bar);
     for (int64_t tl = blockIdx.x; tl < n_tiles; tl += gridDim.x) {
         const int64_t row0 = tl * kTcRows;
         const int rows = (int)min((int64_t)kTcRows, N - row0);
-        __syncthreads();
-        stage_tile(tile, pitch, data + row0 * D, rows, D, vec_ok && rows == kTcRows, t, kTcThreads);
-        if (rows < kTcRows)                              // rows past the end: finite zeros
+        if (bulk_ok(tl)) {
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+        } else {                                         // ragged last tile or unaligned matrix
+            stage_tile(tile, pitch, data + row0 * D, rows, D, false, t, kTcThreads);
             for (int i = rows * pitch + t; i < kTcRows * pitch; i += kTcThreads) tile[i] = 0.f;
+        }
         if (kAccumulate) zero_member_bits(bits, K, kTcThreads / 32, t, kTcThreads);
         __syncthreads();
 
@@ -243,6 +293,7 @@ kmeans_step_tc_kernel(const float *__restrict__ data, int64_t N, int D, const fl
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const float nx = so.nx[mt][h];
+                const float nx_term = 4.76837158203125e-7f * nx * nx * 1.0001f;        // 2^-21 |x'|^2
                 float up = INFINITY;
                 float lo[16];
 #pragma unroll
@@ -251,7 +302,8 @@ kmeans_step_tc_kernel(const float *__restrict__ data, int64_t N, int D, const fl
                     for (int c = 0; c < 2; ++c) {
                         const int n = 8 * j + 2 * tq + c;
                         const float gk = so.g[mt][j][2 * h + c];
-                        const float e = screen_bound(nx, nc[n]);
+                        const float2 ab = *reinterpret_cast<const float2 *>(eab + 2 * n);
+                        const float e = screen_bound(nx, nx_term, ab.x, ab.y);
                         up = fminf(up, gk + e);
                         lo[2 * j + c] = gk - e;
                     }
@@ -276,7 +328,7 @@ kmeans_step_tc_kernel(const float *__restrict__ data, int64_t N, int D, const fl
                     // bound check: (g_k - g_0) vs float64 (d2_k - d2_0), tolerance E_k + E_0
                     const int r = warp * 32 + mt * 16 + g + 8 * h;
                     const float g0 = __shfl_sync(0xffffffffu, so.g[mt][0][2 * h], lane & ~3);
-                    const float e0 = screen_bound(nx, nc[0]);
+                    const float e0 = screen_bound(nx, nx_term, eab[0], eab[1]);
                     if (r < rows) {
                         const float *x = tile + r * pitch;
                         const double d0 = sqdist_scipy(centroids, x, D);
@@ -288,7 +340,7 @@ kmeans_step_tc_kernel(const float *__restrict__ data, int64_t N, int D, const fl
                                 if (n >= K) continue;
                                 const double dk = sqdist_scipy(centroids + (size_t)n * D, x, D);
                                 const double err = fabs(((double)so.g[mt][j][2 * h + c] - (double)g0) - (dk - d0));
-                                const double tol = (double)screen_bound(nx, nc[n]) + (double)e0;
+                                const double tol = (double)screen_bound(nx, nx_term, eab[2 * n], eab[2 * n + 1]) + (double)e0;
                                 if (!(err <= tol)) ++n_viol;
                             }
                     }
@@ -304,10 +356,19 @@ kmeans_step_tc_kernel(const float *__restrict__ data, int64_t N, int D, const fl
             mine = refine_row(mask, tile + t * pitch, centroids, D, eps);
             labels[row0 + t] = mine;
         }
-        if (!kAccumulate) continue;
-        tile_member_bits(bits, mine, kTcThreads / 32, lane, warp);
-        __syncthreads();
-        accumulate_tile(acc, tile, pitch, bits, K, D, lane, warp, kTcThreads / 32);
+        if (kAccumulate) {
+            const unsigned same = tile_member_bits(bits, mine, kTcThreads / 32, lane, warp);
+            __syncthreads();
+            if (warp == 0) tile_cluster_starts(bits, cstart, K, kTcThreads / 32, lane);
+            __syncthreads();
+            tile_row_order(bits, cstart, order, mine, same, kTcThreads / 32, t, lane, warp);
+            __syncthreads();
+            accumulate_tile(acc, tile, pitch, cstart, order, K, D, lane, warp, kTcThreads / 32);
+        }
+        __syncthreads();                                 // every reader of the tile is done
+        const int64_t nxt = tl + gridDim.x;
+        if (t == 0 && nxt < n_tiles && bulk_ok(nxt))
+            bulk_load_tile(tile, data + nxt * kTcRows * D, tile_bytes, bar);
     }
     if (kAccumulate) {
         __syncthreads();
@@ -332,7 +393,7 @@ static int launch_tc_t(const float *data, int64_t N, int D, const float *centroi
     const TcSmem L = tc_layout(D, K, kAcc);
     if (L.total > 227 * 1024) return fail(GSL_EINVAL, "kmeans (tensor-core screening): %zu B of shared memory", L.total);
     GSL_CUDA_TRY(cudaFuncSetAttribute(kmeans_step_tc_kernel<kAcc, kCheck>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-    const int vec_ok = (((uintptr_t)data & 15) == 0) && (((size_t)kTcRows * D) % 4 == 0);
+    const int vec_ok = (((uintptr_t)data & 15) == 0);        // 256 rows x D floats is always a multiple of 16 bytes
     const float eps = (float)((D + 12) * 5.9604644775390625e-08);
     kmeans_step_tc_kernel<kAcc, kCheck><<<grid, kTcThreads, L.total, st>>>(data, N, D, centroids, K, labels, partials, L, vec_ok, eps, check_out);
     GSL_LAUNCH_CHECK("kmeans_step_tc_kernel");
