@@ -32,6 +32,8 @@ constexpr int kTcThreads = 256;          // 8 warps x 32 rows
 constexpr int kTcRows = 256;
 constexpr int kTcKP = 64;                // centroids padded to 64 (8 n-tiles)
 constexpr int kTcCPitch = 68;            // c' row pitch: 68 % 32 == 4 -> conflict-free B fragments
+constexpr int kTcPairs = 32;             // (row, candidate) pairs a warp refines cooperatively per tile;
+                                         // 32 * (4 + 2) B fit in the warp's 32 candidate-mask slots, which they reuse
 
 struct TcSmem {
     size_t acc, cprime, cn2, nc, mean, tile, lab, mask, bar, total;
@@ -50,7 +52,7 @@ static inline TcSmem tc_layout(int D, int K, bool accumulate)
     s.cn2 = o;    o += kTcKP * sizeof(float);
     s.nc = o;     o += 2 * kTcKP * sizeof(float);
     s.mean = o;   o += 64 * sizeof(float);
-    s.tile = o;   o += align_up((size_t)kTcRows * s.pitch * sizeof(float) + 64, 16);   // + slack past the last row
+    s.tile = o;   o += align_up((size_t)kTcRows * s.pitch * sizeof(float), 16);
     s.lab = o;    o += accumulate ? align_up((size_t)K * (kTcThreads / 32) * sizeof(unsigned) + (size_t)(K + 2) * 2 + (size_t)kTcRows * 2, 16) : 0;   // member bits [K][warps], cstart[K+1], order[rows]
     s.mask = o;   o += kTcRows * sizeof(unsigned long long);
     s.bar = o;    o += 16;                                   // mbarrier of the bulk copy
@@ -210,6 +212,73 @@ __device__ __forceinline__ int refine_row(unsigned long long mask, const float *
     return mine;
 }
 
+__device__ __forceinline__ float sqdist_f32(const float *__restrict__ x, const float *__restrict__ c, int D)
+{
+    float s = 0.f;
+    for (int d = 0; d < D; ++d) {
+        const float df = x[d] - __ldg(c + d);
+        s = fmaf(df, df, s);
+    }
+    return s;
+}
+
+// Stages B and C for the 32 rows of a warp (lane = row).  Rows with one candidate are done.  The
+// (row, candidate) pairs of the others are pooled and dealt out one per lane, so the float32
+// distances cost one pass over D for the whole warp instead of one pass per candidate of the
+// unluckiest lane.  Falls back to refine_row when the pool would overflow.
+__device__ __forceinline__ int refine_warp(unsigned long long mask, const float *__restrict__ xt, int pitch,
+                                           const float *__restrict__ centroids, int D, float eps,
+                                           unsigned short *__restrict__ pair, float *__restrict__ dist, int lane)
+{
+    const int n = __popcll(mask);
+    const int want = n > 1 ? n : 0;
+    int incl = want;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return __ffsll((long long)mask) - 1;                 // whole warp decided by stage A
+    if (total > kTcPairs) return refine_row(mask, xt + lane * pitch, centroids, D, eps);
+    const int off = incl - want;
+    if (want) {
+        int i = off;
+        for (unsigned long long m = mask; m; m &= m - 1) pair[i++] = (unsigned short)((lane << 8) | (__ffsll((long long)m) - 1));
+    }
+    __syncwarp();
+    for (int p = lane; p < total; p += 32) {
+        const unsigned pr = pair[p];
+        dist[p] = sqdist_f32(xt + (pr >> 8) * pitch, centroids + (size_t)(pr & 0xffu) * D, D);
+    }
+    __syncwarp();
+    int mine = __ffsll((long long)mask) - 1;
+    if (want) {
+        float s1 = INFINITY, s2 = INFINITY;
+        int k1 = 0;
+        for (int i = off; i < off + want; ++i) {
+            const float s = dist[i];
+            const int k = pair[i] & 0xffu;
+            if (s < s1) { s2 = s1; s1 = s; k1 = k; }
+            else if (s < s2) s2 = s;
+        }
+        if ((s2 * (1.f - eps) > s1 * (1.f + eps)) && (s1 > 1e-30f)) {
+            mine = k1;
+        } else {                                                          // float64, near ties only
+            const float bound = s1 * (1.f + 2.f * eps);
+            double best = INFINITY;
+            mine = 0;                                                     // the float64 scan starts from (inf, 0)
+            for (int i = off; i < off + want; ++i) {
+                if (!(dist[i] * (1.f - 2.f * eps) <= bound) && (s1 > 1e-30f)) continue;
+                const int k = pair[i] & 0xffu;
+                const double d2 = sqdist_scipy(centroids + (size_t)k * D, xt + lane * pitch, D);
+                if (d2 < best) { best = d2; mine = k; }
+            }
+        }
+    }
+    __syncwarp();
+    return mine;
+}
+
 template <bool kAccumulate, bool kCheck>
 __global__ void __launch_bounds__(kTcThreads, 2)
 kmeans_step_tc_kernel(const float *__restrict__ data, int64_t N, int D, const float *__restrict__ centroids,
@@ -350,11 +419,17 @@ kmeans_step_tc_kernel(const float *__restrict__ data, int64_t N, int D, const fl
 
         // ---- stages B, C: lane = row
         int mine = -1;
-        if (t < rows) {
-            const unsigned long long mask = maskbuf[t];
-            if (kCheck) n_cand += __popcll(mask);
-            mine = refine_row(mask, tile + t * pitch, centroids, D, eps);
-            labels[row0 + t] = mine;
+        {
+            const unsigned long long mask = t < rows ? maskbuf[t] : 1ull;  // rows past the end: decided, ignored
+            __syncwarp();                                 // masks are in registers: their slots become the work list
+            if (kCheck && t < rows) n_cand += __popcll(mask);
+            float *distbuf = reinterpret_cast<float *>(maskbuf + warp * 32);
+            unsigned short *pairbuf = reinterpret_cast<unsigned short *>(distbuf + kTcPairs);
+            const int k = refine_warp(mask, tile + warp * 32 * pitch, pitch, centroids, D, eps, pairbuf, distbuf, lane);
+            if (t < rows) {
+                mine = k;
+                labels[row0 + t] = mine;
+            }
         }
         if (kAccumulate) {
             const unsigned same = tile_member_bits(bits, mine, kTcThreads / 32, lane, warp);
