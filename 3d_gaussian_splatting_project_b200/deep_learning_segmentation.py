@@ -162,6 +162,66 @@ def _stage_maps(seg_maps, shapes, device, label_min, n_classes):
     return packed, label_min, n_classes
 
 
+_copy_streams = {}
+
+
+def _lift_pipelined(pos, views, seg_maps, shapes, device):
+    """One-process fast path of lift_labels: the maps are uploaded 16 views at a time on a copy
+    stream while the compute stream packs and sweeps the previous 16 (gsl_lift_prepare +
+    gsl_lift_gather_range), so everything but the last window hides behind the PCIe transfer and
+    only two 16-view staging buffers exist on the device.  Codes are label + 2 (label_min = -1);
+    returns None when the labels do not fit that window and the caller must take the general path."""
+    from ._native import check, lib
+    L = lib()
+    N, V = pos.shape[0], len(views)
+    sizes = [h * w for h, w in shapes]
+    starts = np.concatenate(([0], np.cumsum(sizes))).astype(np.int64)
+    packed = torch.empty(int(starts[-1]), dtype=torch.uint8, device=device)
+    ws = ops._ws.get(device, L.gsl_lift_workspace_bytes(N, V))
+    main = torch.cuda.current_stream(device)
+    key = (device.type, device.index)
+    if key not in _copy_streams:
+        _copy_streams[key] = torch.cuda.Stream(device)
+    copy = _copy_streams[key]
+    CH = 16
+    chunk_px = max(int(starts[min(v0 + CH, V)] - starts[v0]) for v0 in range(0, V, CH))
+    slots = [torch.empty(chunk_px, dtype=torch.int32, device=device) for _ in range(2)]
+    slot_free = [None, None]
+    minmax = torch.tensor([2**31 - 1, -2**31], dtype=torch.int32, device=device)
+    err = torch.zeros(1, dtype=torch.int32, device=device)
+    vptr = views.ctypes.data
+    with torch.cuda.device(device):
+        check(L.gsl_lift_prepare(pos.data_ptr(), N, vptr, V, ws.data_ptr(), ws.numel(), main.cuda_stream))
+        for ci, v0 in enumerate(range(0, V, CH)):
+            v1 = min(v0 + CH, V)
+            buf = slots[ci % 2]
+            with torch.cuda.stream(copy):
+                if slot_free[ci % 2] is not None:
+                    copy.wait_event(slot_free[ci % 2])
+                off = 0
+                for v in range(v0, v1):
+                    m = seg_maps[v]
+                    src = m if isinstance(m, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(m, np.int32))
+                    buf[off:off + sizes[v]].copy_(src.reshape(-1), non_blocking=True)
+                    off += sizes[v]
+                ready = torch.cuda.Event()
+                ready.record(copy)
+            main.wait_event(ready)
+            check(L.gsl_label_range(buf.data_ptr(), off, minmax.data_ptr(), main.cuda_stream))
+            check(L.gsl_pack_labels(buf.data_ptr(), packed.data_ptr() + int(starts[v0]), off, -1, 255,
+                                    err.data_ptr(), main.cuda_stream))
+            slot_free[ci % 2] = torch.cuda.Event()
+            slot_free[ci % 2].record(main)
+            check(L.gsl_lift_gather_range(pos.data_ptr(), N, vptr, V, v0, v1, packed.data_ptr(), None, 0.0, 0,
+                                          ws.data_ptr(), ws.numel(), main.cuda_stream))
+        lo, hi = (int(x) for x in minmax.tolist())           # synchronises: every copy has been consumed
+        if lo < -1 or hi > 253:
+            return None
+        labels = torch.empty(N, dtype=torch.int32, device=device)
+        check(L.gsl_lift_majority(N, V, -1, max(hi + 2, 1), labels.data_ptr(), ws.data_ptr(), ws.numel(), main.cuda_stream))
+    return labels
+
+
 def lift_labels(positions, cameras, seg_maps, image_sizes=None, device=None, want_near=False,
                 near_eps=1e-4, label_min=None, n_classes=None):
     """Majority-vote labels for `positions` given one segmentation map per camera.
@@ -177,11 +237,27 @@ def lift_labels(positions, cameras, seg_maps, image_sizes=None, device=None, wan
     pos = pos.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
     shapes = [tuple(m.shape) for m in seg_maps]
     views = ops.make_views(cameras, shapes, image_sizes)
+    import torch.distributed as dist
+    single = not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
+    if (single and not want_near and label_min is None and n_classes is None and len(views) and pos.shape[0]
+            and all(int(np.prod(sh)) % 4 == 0 for sh in shapes)):
+        fast = _lift_pipelined(pos, views, seg_maps, shapes, device)
+        if fast is not None:
+            return _to_host(fast)
     packed, label_min, n_classes = _stage_maps(seg_maps, shapes, device, label_min, n_classes)
     res = ops.lift_votes(pos, views, packed, label_min, n_classes, want_near=want_near, near_eps=near_eps)
     if want_near:
-        return res[0].cpu().numpy(), res[1].cpu().numpy()
-    return res.cpu().numpy()
+        return _to_host(res[0]), _to_host(res[1])
+    return _to_host(res)
+
+
+def _to_host(t: torch.Tensor) -> np.ndarray:
+    """Device tensor -> NumPy through a pinned staging tensor (a pageable `.cpu()` of 24 MB costs
+    ~10 ms; pinned, it is PCIe speed).  The array owns its pinned storage."""
+    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    host.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return host.numpy()
 
 
 def assign_labels(gaussians, cameras, input_dir, output_dir, model_type="mask2former", segmenter=None):

@@ -119,6 +119,19 @@ int gsl_lift_votes(const float *pos, int64_t N, const GslView *views, int V,
 int gsl_lift_gather(const float *pos, int64_t N, const GslView *views, int V,
                     const uint8_t *packed, uint8_t *near, double near_eps, int view_window,
                     void *ws, size_t ws_bytes, void *stream);
+/*
+ * gsl_lift_gather in two steps, so that views can be swept while later maps are still being
+ * uploaded: prepare orders the Gaussians and decides which (tile, view) pairs can be skipped (it
+ * reads camera parameters only, no maps); gather_range sweeps views [v_begin, v_end), v_begin a
+ * multiple of 16, whose packed maps must be resident.  gsl_lift_gather == prepare + range(0, V).
+ * `near` (if used) must be zeroed by the caller before the first range.
+ */
+int gsl_lift_prepare(const float *pos, int64_t N, const GslView *views, int V,
+                     void *ws, size_t ws_bytes, void *stream);
+int gsl_lift_gather_range(const float *pos, int64_t N, const GslView *views, int V,
+                          int v_begin, int v_end, const uint8_t *packed,
+                          uint8_t *near, double near_eps, int view_window,
+                          void *ws, size_t ws_bytes, void *stream);
 int gsl_lift_majority(int64_t N, int V, int label_min, int n_classes, int32_t *labels,
                       const void *ws, size_t ws_bytes, void *stream);
 
