@@ -15,6 +15,12 @@ struct DevView {
     GslView g;
     int unit_scale;    // scale_x == 1 && scale_y == 1: the rescale of dls:281-282 is the identity
     int no_clamp;      // unit scale and the map covers the camera frame: dls:285-286 cannot fire
+    // float32 screening (lift.cu: screen_pair): the camera rounded to float32 and the two
+    // constants of the error bound  Ec = g_rm * (|X|+|Y|+|Z|) + g_tm  on a camera coordinate
+    int screen_ok;     // bounds are integers below 2^21 and every parameter is finite
+    float R[9], t[3], fx, fy, half_w, half_h;
+    float fx_abs, fy_abs, g_rm, g_tm;
+    int wi, hi;        // width, height as integers
 };
 
 // A window of views travels as a kernel parameter (constant bank 0, compile-time offsets).

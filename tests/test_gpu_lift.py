@@ -204,6 +204,14 @@ def test_full_size_c3_properties_and_oracle(oracle):
     full = ops.lift_votes(d_pos, views, packed).cpu().numpy()
     again = ops.lift_votes(d_pos, views, packed).cpu().numpy()
     assert np.array_equal(full, again)
+    # float32 screening (opt-in) and ordering+culling (default) are execution strategies only
+    for var, val in (("GSLIFT_LIFT_SCREEN", "1"), ("GSLIFT_LIFT_ORDER", "0")):
+        os.environ[var] = val
+        try:
+            plain = ops.lift_votes(d_pos, views, packed).cpu().numpy()
+        finally:
+            del os.environ[var]
+        assert np.array_equal(plain, full), f"{var}={val} changes {(plain != full).sum()} labels"
     lo, hi = 375_000, 500_000                           # rank 3 of 8
     part = ops.lift_votes(d_pos[lo:hi].contiguous(), views, packed).cpu().numpy()
     assert np.array_equal(part, full[lo:hi])
