@@ -1,0 +1,78 @@
+"""The two reference entry points, run as scripts with the reference's flags on a stand-in scene
+(config C1 / C2 shape, small): outputs are labelled PLY files the reference's viewer can read."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from util import load_lift_case, pkg
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _standin_ply(path, n, seed):
+    scene, plyio = pkg("scene"), pkg("plyio")
+    v = scene.standin_3dgs_vertices(n, seed=seed)
+    plyio.write_ply(path, [("vertex", v)], text=False)
+    return v
+
+
+def test_k_means_script_c1(oracle, tmp_path):
+    """python 3D_clustering/k_means.py --file_path .. --save_path .. [--k 10]  (k_means.py:198-215)"""
+    plyio = pkg("plyio")
+    src, dst = tmp_path / "point_cloud.ply", tmp_path / "clustered.ply"
+    v = _standin_ply(src, 20000, seed=1)
+    code = ("import numpy as np, runpy, sys; np.random.seed(0); sys.argv = sys.argv[1:]; "
+            "runpy.run_path(sys.argv[0], run_name='__main__')")
+    out = subprocess.run([sys.executable, "-c", code, os.path.join(ROOT, "3D_clustering", "k_means.py"),
+                          "--file_path", str(src), "--save_path", str(dst)], capture_output=True, text=True, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = out.stdout.splitlines()
+    assert f"New PLY file with label added saved to {dst}" in lines[-1]
+    assert sum(1 for ln in lines if ln.strip().isdigit()) == 10          # max_iter=10, one index per iteration
+    back = plyio.read_ply(dst)
+    assert back.text and back["vertex"].data.dtype.names[-1] == "label"
+    got = back["vertex"]["label"]
+    # the oracle's run of the same algorithm from the same seeded start
+    data = np.column_stack((v["x"], v["y"], v["z"], v["f_dc_0"], v["f_dc_1"], v["f_dc_2"])).astype(np.float32)
+    np.random.seed(0)
+    _, want, _ = oracle.kmeans_run(data, 10, max_iter=10)
+    assert np.array_equal(got.astype(np.int64), want)
+    for name in ("x", "f_dc_2", "rot_3"):
+        assert np.array_equal(back["vertex"][name], v[name])              # %.18g round-trips float32
+
+
+def test_lifting_script_c2(oracle, tmp_path):
+    """python deep_learning_segmentation.py --ply_file .. --camera_file .. --input_dir .. --output_dir ..
+    --output_file ..  with the bundled cameras and precomputed <img>_segmap.npy files (:165, :335-375)."""
+    from PIL import Image
+    plyio = pkg("plyio")
+    c = load_lift_case("lift_bundled_halfres")
+    src, dst = tmp_path / "scene.ply", tmp_path / "labelled.ply"
+    v = _standin_ply(src, 30000, seed=2)
+    v["x"] *= 2; v["y"] *= 2; v["z"] *= 2
+    plyio.write_ply(src, [("vertex", v)], text=False)
+    img_dir, seg_dir = tmp_path / "images", tmp_path / "seg"
+    os.makedirs(img_dir); os.makedirs(seg_dir)
+    json.dump(c["cameras"], open(tmp_path / "cameras.json", "w"))
+    for cam, m, (w, h) in zip(c["cameras"], c["maps"], c["sizes"]):
+        Image.new("L", (w, h)).save(img_dir / (cam["img_name"] + ".png"))
+        np.save(seg_dir / f"{cam['img_name']}_segmap.npy", m)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "deep_learning_segmentation.py"), "--ply_file", str(src),
+                          "--camera_file", str(tmp_path / "cameras.json"), "--input_dir", str(img_dir),
+                          "--output_dir", str(seg_dir), "--output_file", str(dst)], capture_output=True, text=True, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "Loading cameras..." in out.stdout and "Label statistics:" in out.stdout
+    assert out.stdout.count("Processing image") == len(c["cameras"])
+    back = plyio.read_ply(dst)
+    assert not back.text and back["vertex"].data.dtype.names[-1] == "label"
+    pos = np.column_stack((v["x"], v["y"], v["z"])).astype(np.float32)
+    want, _, vis = oracle.lift_votes(pos, oracle.make_views(c["cameras"], c["shapes"], c["sizes"]), c["flat"])
+    assert np.array_equal(back["vertex"]["label"], want)
+    assert f"Total gaussians: {len(pos)}" in out.stdout
+    n_unseen = int((want == -1).sum())
+    assert f"Label -1: {n_unseen} gaussians" in out.stdout
