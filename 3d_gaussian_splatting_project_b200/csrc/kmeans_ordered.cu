@@ -11,9 +11,9 @@
 //   ordered_start_kernel     exclusive scan of the totals -> segment starts
 //   ordered_scatter_kernel   stable scatter of row indices into per-cluster member lists
 //                            (warp match_any ranks keep ascending row order)
-//   ordered_chain_kernel     CTA per (cluster, 32 dims): all warps prefetch the next 256
-//                            member rows while warp 0 adds the current 256 in order,
-//                            lane = dimension
+//   ordered_chain_kernel     CTA per (cluster, 32 dims): seven producer warps cp.async member rows
+//                            into a 4-deep shared-memory ring while warp 0 adds them in
+//                            order, lane = dimension
 //   shift_kernel             ||new - old||_F
 //
 // This is the parity mode (single device).  The throughput mode is gsl_kmeans_step's float64
@@ -24,7 +24,6 @@ namespace gsl {
 
 constexpr int kOrdTile = 1024;
 constexpr int kOrdThreads = 256;
-constexpr int kChainBatch = 256;   // members per prefetch batch (32 per warp)
 
 __global__ void __launch_bounds__(kOrdThreads)
 ordered_count_kernel(const int32_t *__restrict__ labels, int64_t N, int K, int32_t *__restrict__ tile_counts)
@@ -114,13 +113,25 @@ ordered_scatter_kernel(const int32_t *__restrict__ labels, int64_t N, int K,
     }
 }
 
-// grid (K, ceil(D/32)); lane = dimension d0 + lane.
+// grid (K, ceil(D/32)); lane = dimension d0 + lane.  Warp 0 is the consumer: it owns the K*D/32
+// float32 accumulators of this (cluster, dimension chunk) and adds member rows strictly in index
+// order.  Warps 1..7 are producers: they gather the member rows (128 bytes per row and chunk) with
+// cp.async straight into a ring of kChainRing shared-memory batches, three batches ahead of the
+// consumer, so the DRAM latency of the row gather is hidden behind the dependent add chain.
+constexpr int kChainRows = 7 * 32;     // rows per batch: 32 per producer warp
+constexpr int kChainRing = 4;
+
+__device__ __forceinline__ void cp_async_4(float *dst, const float *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+
 __global__ void __launch_bounds__(kOrdThreads)
 ordered_chain_kernel(const float *__restrict__ data, int D, const int32_t *__restrict__ members,
                      const int64_t *__restrict__ start, const int64_t *__restrict__ total,
                      const float *__restrict__ old_c, float *__restrict__ new_c)
 {
-    extern __shared__ float buf[];              // [2][kChainBatch][32]
+    extern __shared__ float buf[];              // [kChainRing][kChainRows][32]
     const int k = blockIdx.x, d = blockIdx.y * 32 + (threadIdx.x & 31);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t n = total[k], s0 = start[k];
@@ -129,45 +140,41 @@ ordered_chain_kernel(const float *__restrict__ data, int D, const int32_t *__res
         if (w == 0 && live) new_c[(size_t)k * D + d] = old_c[(size_t)k * D + d];   // km:126 else-branch
         return;
     }
-    float v[32];
-    auto fetch = [&](int64_t b0) {   // this warp's 32 rows of the batch starting at member b0
-        const int64_t mi = b0 + w * 32 + lane;
-        const int idx = mi < n ? members[s0 + mi] : -1;
+    const int64_t n_batches = (n + kChainRows - 1) / kChainRows;
+    auto issue = [&](int64_t b) {               // producers: this warp's 32 rows of batch b
+        if (w > 0 && b < n_batches) {
+            const int64_t mi = b * kChainRows + (w - 1) * 32 + lane;
+            const int idx = mi < n ? members[s0 + mi] : -1;
+            float *dst = buf + ((size_t)(b % kChainRing) * kChainRows + (size_t)(w - 1) * 32) * 32 + lane;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const int r = __shfl_sync(0xffffffffu, idx, j);
-            v[j] = (r >= 0 && live) ? __ldcs(data + (size_t)r * D + d) : 0.f;
+            for (int j = 0; j < 32; ++j) {
+                const int r = __shfl_sync(0xffffffffu, idx, j);
+                if (r >= 0 && live) cp_async_4(dst + j * 32, data + (size_t)r * D + d);
+            }
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    auto stash = [&](int which) {
-        float *dst = buf + (size_t)which * kChainBatch * 32 + (size_t)(w * 32) * 32 + lane;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) dst[j * 32] = v[j];
-    };
-    fetch(0);
-    stash(0);
-    __syncthreads();
+    for (int p = 0; p < kChainRing - 1; ++p) issue(p);
     float acc = -0.0f;              // (-0) + x == x for every x: same as starting from the first row
-    int cur = 0;
-    for (int64_t b0 = 0; b0 < n; b0 += kChainBatch) {
-        const bool more = b0 + kChainBatch < n;
-        if (more) fetch(b0 + kChainBatch);                 // loads in flight during the chain
-        if (w == 0) {
-            const int cnt = (int)min((int64_t)kChainBatch, n - b0);
-            const float *src = buf + (size_t)cur * kChainBatch * 32 + lane;
+    for (int64_t b = 0; b < n_batches; ++b) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(kChainRing - 2) : "memory");   // my part of batch b landed
+        __syncthreads();            // everyone's part landed; the consumer is done with batch b - 1
+        issue(b + kChainRing - 1);  // refills the slot batch b - 1 occupied
+        if (w == 0 && live) {
+            const int cnt = (int)min((int64_t)kChainRows, n - b * kChainRows);
+            const float *src = buf + (size_t)(b % kChainRing) * kChainRows * 32 + lane;
+            // the adds are one dependent chain (4 cycles each); the shared loads are batched 32
+            // deep so that their latency is paid once per 32 adds
             int i = 0;
-            for (; i + 8 <= cnt; i += 8) {
-                float x[8];
+            for (; i + 32 <= cnt; i += 32) {
+                float x[32];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) x[j] = src[(i + j) * 32];
+                for (int j = 0; j < 32; ++j) x[j] = src[(i + j) * 32];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc = __fadd_rn(acc, x[j]);
+                for (int j = 0; j < 32; ++j) acc = __fadd_rn(acc, x[j]);
             }
             for (; i < cnt; ++i) acc = __fadd_rn(acc, src[i * 32]);
         }
-        if (more) stash(cur ^ 1);
-        __syncthreads();
-        cur ^= 1;
     }
     if (w == 0 && live) new_c[(size_t)k * D + d] = (float)((double)acc / (double)n);
 }
@@ -245,7 +252,7 @@ extern "C" int gsl_kmeans_update_ordered(const float *data, const int32_t *label
         ordered_scatter_kernel<<<n_tiles, kOrdThreads, sc_smem, st>>>(labels, N, K, tile_counts, start, members);
         GSL_LAUNCH_CHECK("ordered_scatter_kernel");
     }
-    const size_t ch_smem = (size_t)2 * kChainBatch * 32 * sizeof(float);
+    const size_t ch_smem = (size_t)kChainRing * kChainRows * 32 * sizeof(float);
     GSL_CUDA_TRY(cudaFuncSetAttribute(ordered_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch_smem));
     dim3 grid((unsigned)K, (unsigned)((D + 31) / 32));
     ordered_chain_kernel<<<grid, kOrdThreads, ch_smem, st>>>(data, D, members, start, total, old_centroids, new_centroids);

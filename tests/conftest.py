@@ -12,6 +12,18 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_sessionstart(session):
+    """Build libgslift.so (nvcc, sm_100a) and the C oracle if they are missing, e.g. on a fresh
+    checkout: both are git-ignored build products.  A stale-but-present library is left alone
+    here (the GPU box receives the prebuilt files and may have no reason to rebuild)."""
+    import importlib
+    builder = importlib.import_module("3d_gaussian_splatting_project_b200.build")
+    if not os.path.exists(builder.LIB):
+        builder.build()
+    from oracle import oracle as orc
+    orc.build()
+
+
 @pytest.fixture(scope="session")
 def oracle():
     from oracle import oracle as orc
