@@ -31,7 +31,7 @@ struct ViewWindow {
 
 // Byte offsets of the pieces of the lifting workspace (each 256-byte aligned).
 struct OrderWs {
-    size_t sheet, pos_sorted, perm, cell, hist, bbox, tilebox, masks, views, bytes;
+    size_t sheet, pos_sorted, perm, cell, hist, bbox, tilebox, masks, views, planes, bytes;
 };
 
 OrderWs order_layout(int64_t N, int V);

@@ -8,7 +8,7 @@
 // only ~13 % of (Gaussian, view) pairs are visible, so this removes most of the work; on the
 // synthetic look-at scenes it removes the ~25 % that is invisible.  Labels are unaffected: the
 // gather kernel still evaluates the reference's exact test for every pair it does not skip, and
-// the cull is conservative (margins 10^6 times the float64 rounding error).
+// the cull is conservative (margins ten times its own float32 rounding error, never the other way).
 //
 //   order_bbox_kernel     min/max of the finite coordinates (ordered-uint atomics)
 //   order_cell_kernel     16^3 grid over the box, cell id = 12-bit Morton code (non-finite
@@ -19,6 +19,7 @@
 //                         with one global atomic and ranks its rows inside it in shared memory.
 //                         The order inside a cell depends on atomic arrival; results do not.
 //   order_tilebox_kernel  bounding box (+ non-finite flag) of each run of 256 sorted Gaussians
+//   order_planes_kernel   per view, the five half-spaces of the visibility test as linear forms
 //   order_cull_kernel     one bit per (tile, view), 16 views to a mask word, all views in one launch
 #include "common.cuh"
 #include "lift_internal.cuh"
@@ -198,62 +199,74 @@ order_tilebox_kernel(const float *__restrict__ pos_sorted, int64_t N, int64_t n_
     }
 }
 
-// max / min over the box of  a.X + c
-__device__ __forceinline__ void lin_range(const double (&a)[3], double c, const double (&lo)[3], const double (&hi)[3],
-                                          double &mn, double &mx, double &mag)
+// The five half-spaces that bound "can pass the reference's visibility test" (dls:72, :80), as
+// linear forms a.X + c of the world position, per view, in float32:
+//   p0  cz                                   visible needs  > 0
+//   p1  fx*cx + half_w*cz                    x >= 0      <=>  p1 >= 0      (cz > 0)
+//   p2  fx*cx + (half_w - width)*cz          x <  width  <=>  p2 <  0
+//   p3  fy*cy + half_h*cz                    y >= 0      <=>  p3 >= 0
+//   p4  fy*cy + (half_h - height)*cz         y <  height <=>  p4 <  0
+// planes[v][p] = {a0, a1, a2, c}.  A view with a non-finite parameter gets NaN planes, which
+// never cull.
+__global__ void __launch_bounds__(128)
+order_planes_kernel(const GslView *__restrict__ views, int V, float4 *__restrict__ planes)
 {
-    mn = c; mx = c; mag = fabs(c);
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    const GslView w = views[v];
+    const double kx[5] = {0.0, w.fx, w.fx, 0.0, 0.0};
+    const double ky[5] = {0.0, 0.0, 0.0, w.fy, w.fy};
+    const double kz[5] = {1.0, w.half_w, w.half_w - w.width, w.half_h, w.half_h - w.height};
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        const double p = a[j] * lo[j], q = a[j] * hi[j];
-        mn += fmin(p, q); mx += fmax(p, q);
-        mag += fmax(fabs(p), fabs(q));
+    for (int p = 0; p < 5; ++p) {
+        float4 o;
+        o.x = (float)(kx[p] * w.R[0] + ky[p] * w.R[3] + kz[p] * w.R[6]);
+        o.y = (float)(kx[p] * w.R[1] + ky[p] * w.R[4] + kz[p] * w.R[7]);
+        o.z = (float)(kx[p] * w.R[2] + ky[p] * w.R[5] + kz[p] * w.R[8]);
+        o.w = (float)(kx[p] * w.t[0] + ky[p] * w.t[1] + kz[p] * w.t[2]);
+        planes[v * 5 + p] = o;
     }
 }
 
-// Can any point of the box pass the reference's visibility test (dls:72, :80) in this view?
-// Conservative: answers "no" only with margins far above the float64 rounding of the kernel.
-__device__ __forceinline__ bool box_may_be_visible(const GslView &w, const double (&lo)[3], const double (&hi)[3])
+// range of a.X + c over the box, and the magnitude that scales its rounding error
+__device__ __forceinline__ void lin_range(const float4 pl, const float (&lo)[3], const float (&hi)[3],
+                                          float &mn, float &mx, float &mag)
 {
-    const double rel = 1e-9, px = 1e-6;
-    double mn, mx, mag;
-    const double r2[3] = {w.R[6], w.R[7], w.R[8]};
-    lin_range(r2, w.t[2], lo, hi, mn, mx, mag);
-    const double czmax = mx;
-    if (czmax < -(rel * mag + 1e-300)) return false;                       // every point has z <= 0
-    const double zpos = fmax(czmax, 0.0);
-    // x < 0  <=>  fx*cx + half_w*cz < 0   (cz > 0)
-    double a[3], c;
+    const float a[3] = {pl.x, pl.y, pl.z};
+    mn = pl.w; mx = pl.w; mag = fabsf(pl.w);
 #pragma unroll
-    for (int j = 0; j < 3; ++j) a[j] = w.fx * w.R[j] + w.half_w * w.R[6 + j];
-    c = w.fx * w.t[0] + w.half_w * w.t[2];
-    lin_range(a, c, lo, hi, mn, mx, mag);
-    if (mx < -(px * zpos + rel * mag)) return false;
-    // x >= width  <=>  fx*cx + (half_w - width)*cz >= 0
-#pragma unroll
-    for (int j = 0; j < 3; ++j) a[j] = w.fx * w.R[j] + (w.half_w - w.width) * w.R[6 + j];
-    c = w.fx * w.t[0] + (w.half_w - w.width) * w.t[2];
-    lin_range(a, c, lo, hi, mn, mx, mag);
-    if (mn > px * zpos + rel * mag) return false;
-    // y < 0
-#pragma unroll
-    for (int j = 0; j < 3; ++j) a[j] = w.fy * w.R[3 + j] + w.half_h * w.R[6 + j];
-    c = w.fy * w.t[1] + w.half_h * w.t[2];
-    lin_range(a, c, lo, hi, mn, mx, mag);
-    if (mx < -(px * zpos + rel * mag)) return false;
-    // y >= height
-#pragma unroll
-    for (int j = 0; j < 3; ++j) a[j] = w.fy * w.R[3 + j] + (w.half_h - w.height) * w.R[6 + j];
-    c = w.fy * w.t[1] + (w.half_h - w.height) * w.t[2];
-    lin_range(a, c, lo, hi, mn, mx, mag);
-    if (mn > px * zpos + rel * mag) return false;
-    return true;                                                            // NaN anywhere ends up here
+    for (int j = 0; j < 3; ++j) {
+        const float p = a[j] * lo[j], q = a[j] * hi[j];
+        mn += fminf(p, q); mx += fmaxf(p, q);
+        mag += fmaxf(fabsf(p), fabsf(q));
+    }
+}
+
+// Can any point of the box pass the visibility test in this view?  Conservative: float32
+// evaluation (coefficients rounded once, four roundings per form: error < 1e-6 * mag) against
+// margins of 1e-5 * mag plus 1e-6 px, so "no" is only ever said with room to spare; NaN says yes.
+__device__ __forceinline__ bool box_may_be_visible(const float4 *__restrict__ pl, const float (&lo)[3], const float (&hi)[3])
+{
+    const float rel = 1e-5f, px = 1e-6f;
+    float mn, mx, mag;
+    lin_range(pl[0], lo, hi, mn, mx, mag);
+    if (mx < -(rel * mag + 1e-30f)) return false;                          // every point has z <= 0
+    const float zpos = fmaxf(mx, 0.f) * px;
+    lin_range(pl[1], lo, hi, mn, mx, mag);
+    if (mx < -(zpos + rel * mag)) return false;                            // x < 0 everywhere
+    lin_range(pl[2], lo, hi, mn, mx, mag);
+    if (mn > zpos + rel * mag) return false;                               // x >= width everywhere
+    lin_range(pl[3], lo, hi, mn, mx, mag);
+    if (mx < -(zpos + rel * mag)) return false;                            // y < 0 everywhere
+    lin_range(pl[4], lo, hi, mn, mx, mag);
+    if (mn > zpos + rel * mag) return false;                               // y >= height everywhere
+    return true;
 }
 
 // Thread per (tile, view); 16 consecutive lanes share a tile and fill one 16-bit mask word:
 // masks[tile * n_words16 + v / 16], bit v % 16.
 __global__ void __launch_bounds__(256)
-order_cull_kernel(const float *__restrict__ box, int64_t n_tiles, const GslView *__restrict__ views, int V,
+order_cull_kernel(const float *__restrict__ box, int64_t n_tiles, const float4 *__restrict__ planes, int V,
                   uint16_t *__restrict__ masks, int n_words16)
 {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -266,8 +279,8 @@ order_cull_kernel(const float *__restrict__ box, int64_t n_tiles, const GslView 
         if (b[6] != 0.f) {
             vis = true;                                                     // non-finite member: never cull
         } else {
-            const double lo[3] = {b[0], b[1], b[2]}, hi[3] = {b[3], b[4], b[5]};
-            vis = box_may_be_visible(views[v], lo, hi);
+            const float lo[3] = {b[0], b[1], b[2]}, hi[3] = {b[3], b[4], b[5]};
+            vis = box_may_be_visible(planes + (size_t)v * 5, lo, hi);
         }
     }
     const unsigned bal = __ballot_sync(0xffffffffu, vis);
@@ -293,6 +306,7 @@ OrderWs order_layout(int64_t N, int V)
     o.tilebox = take((size_t)n_tiles * 8 * sizeof(float));
     o.masks = take((size_t)n_tiles * (size_t)n_words16 * sizeof(uint16_t));
     o.views = take((size_t)(V > 0 ? V : 1) * sizeof(GslView));
+    o.planes = take((size_t)(V > 0 ? V : 1) * 5 * sizeof(float4));
     o.bytes = off + 256;
     return o;
 }
@@ -310,6 +324,7 @@ int order_gaussians(const float *pos, int64_t N, const GslView *views, int V, un
     float *tilebox = reinterpret_cast<float *>(base + L.tilebox);
     uint16_t *masks = reinterpret_cast<uint16_t *>(base + L.masks);
     GslView *d_views = reinterpret_cast<GslView *>(base + L.views);
+    float4 *planes = reinterpret_cast<float4 *>(base + L.planes);
     const int64_t n_tiles = (N + kSheetTile - 1) / kSheetTile;
     const int n_words16 = (V + 15) / 16;
 
@@ -332,8 +347,10 @@ int order_gaussians(const float *pos, int64_t N, const GslView *views, int V, un
     GSL_LAUNCH_CHECK("order_scatter_kernel");
     order_tilebox_kernel<<<(unsigned)((n_tiles + 7) / 8), 256, 0, st>>>(pos_sorted, N, n_tiles, tilebox);
     GSL_LAUNCH_CHECK("order_tilebox_kernel");
+    order_planes_kernel<<<(V + 127) / 128, 128, 0, st>>>(d_views, V, planes);
+    GSL_LAUNCH_CHECK("order_planes_kernel");
     const int64_t threads = n_tiles * (int64_t)n_words16 * 16;
-    order_cull_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(tilebox, n_tiles, d_views, V, masks, n_words16);
+    order_cull_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(tilebox, n_tiles, planes, V, masks, n_words16);
     GSL_LAUNCH_CHECK("order_cull_kernel");
     return GSL_OK;
 }
