@@ -162,23 +162,34 @@ kmeans_step_kernel(const float *__restrict__ data, int64_t N, int D, const float
     }
 }
 
+// Fixed-order sum of the per-CTA partials.  A block owns 32 consecutive elements; its 8 warps
+// each add the partials p = w, w + 8, ... (coalesced 256-byte rows), then warp 0 adds the eight
+// warp sums in warp order -- the same grouping on every run, so the result is reproducible.
 __global__ void __launch_bounds__(256)
 kmeans_reduce_kernel(const double *__restrict__ partials, int n_parts, int n_el, double *__restrict__ sums)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_el) return;
+    __shared__ double part[8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + lane;
     double s = 0.0;
-    for (int p = 0; p < n_parts; ++p) s += partials[(size_t)p * n_el + i];
-    sums[i] = s;
+    if (i < n_el)
+        for (int p = w; p < n_parts; p += 8) s += partials[(size_t)p * n_el + i];
+    part[w][lane] = s;
+    __syncthreads();
+    if (w == 0 && i < n_el) {
+        double t = part[0][lane];
+        for (int ww = 1; ww < 8; ++ww) t += part[ww][lane];
+        sums[i] = t;
+    }
 }
 
 // One CTA.  new = (float)(sum / count) (float64 quotient, as np.mean's true_divide with an
 // intp count does, km:126) or old when empty; shift = Frobenius norm of the float32 difference.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 kmeans_finalize_kernel(const double *__restrict__ sums, const float *__restrict__ old_c, int K, int D,
                        float *__restrict__ new_c, float *__restrict__ shift)
 {
-    __shared__ double red[8];
+    __shared__ double red[32];
     double sq = 0.0;
     for (int i = threadIdx.x; i < K * D; i += blockDim.x) {
         const int k = i / D, d = i - k * D;
@@ -194,7 +205,7 @@ kmeans_finalize_kernel(const double *__restrict__ sums, const float *__restrict_
     __syncthreads();
     if (threadIdx.x == 0) {
         double s = 0.0;
-        for (int w = 0; w < 8; ++w) s += red[w];
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
         *shift = (float)sqrt(s);
     }
 }
@@ -317,7 +328,7 @@ extern "C" int gsl_kmeans_step(const float *data, int64_t N, int D, const float 
     double *partials = reinterpret_cast<double *>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
     const int grid = step_grid(N);
     if (int rc = launch_step<true>(data, N, D, centroids, K, labels, partials, grid, st)) return rc;
-    kmeans_reduce_kernel<<<(n_el + 255) / 256, 256, 0, st>>>(partials, grid, n_el, sums);
+    kmeans_reduce_kernel<<<(n_el + 31) / 32, 256, 0, st>>>(partials, grid, n_el, sums);
     GSL_LAUNCH_CHECK("kmeans_reduce_kernel");
     return GSL_OK;
 }
@@ -327,7 +338,7 @@ extern "C" int gsl_kmeans_finalize(const double *sums, const float *old_centroid
 {
     if (int rc = check_kd("gsl_kmeans_finalize", 0, D, K)) return rc;
     if (!sums || !old_centroids || !new_centroids || !shift) return fail(GSL_EINVAL, "gsl_kmeans_finalize: null pointer");
-    kmeans_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(sums, old_centroids, K, D, new_centroids, shift);
+    kmeans_finalize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(sums, old_centroids, K, D, new_centroids, shift);
     GSL_LAUNCH_CHECK("kmeans_finalize_kernel");
     return GSL_OK;
 }
