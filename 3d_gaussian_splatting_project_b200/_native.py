@@ -52,6 +52,7 @@ SIGNATURES = {
     "gsl_kmeans_finalize": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "gsl_kmeans_update_ordered": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gsl_kmeans_screen_selftest": (_i32, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp]),
+    "gsl_ply_format_ascii": (_i64, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _i64, _i32]),
     "gsl_recolor": (_i32, [_vp, _i64, _vp, _vp, _vp]),
 }
 

@@ -14,12 +14,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgslift.so")
-SOURCES = ["api.cu", "lift.cu", "lift_order.cu", "kmeans.cu", "kmeans_tc.cu", "kmeans_ordered.cu"]
+SOURCES = ["api.cu", "lift.cu", "lift_order.cu", "kmeans.cu", "kmeans_tc.cu", "kmeans_ordered.cu", "ply_format.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-fmad=false",            # no implicit contraction: fused ops are spelled fma() in the source
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-shared",
     "-I", os.path.join(ROOT, "include"),
 ]
 

@@ -143,16 +143,46 @@ def write_ply(path_or_file, elements, text=False, comments=()):
             names = e.data.dtype.names
             if text:
                 # plyfile: every field of a record goes through '%.18g' as a float64
-                cols = np.column_stack([e.data[n].astype(np.float64) for n in names]) if len(e.data) else np.empty((0, len(names)))
-                chunk = 65536
-                for s in range(0, len(cols), chunk):
-                    np.savetxt(f, cols[s:s + chunk], fmt="%.18g", newline="\n")
+                if not _write_ascii_native(f, e.data):
+                    cols = np.column_stack([e.data[n].astype(np.float64) for n in names]) if len(e.data) else np.empty((0, len(names)))
+                    chunk = 65536
+                    for s in range(0, len(cols), chunk):
+                        np.savetxt(f, cols[s:s + chunk], fmt="%.18g", newline="\n")
             else:
                 packed = np.dtype([(n, "<" + e.data.dtype[n].str.lstrip("<>|=")) for n in names])
                 f.write(np.ascontiguousarray(e.data.astype(packed)).tobytes())
     finally:
         if own:
             f.close()
+
+
+_TYPE_CODE = {"i1": 0, "u1": 1, "i2": 2, "u2": 3, "i4": 4, "u4": 5, "f4": 6, "f8": 7}
+
+
+def _write_ascii_native(f, data) -> bool:
+    """ASCII rows through the multi-threaded C formatter of libgslift.so (gsl_ply_format_ascii).
+    Returns False when the library is not built, so that file I/O keeps working without it (this
+    is host-side formatting, not part of the GPU path)."""
+    import ctypes
+    try:
+        from ._native import lib
+        L = lib()
+    except (ImportError, OSError):
+        return False
+    names = data.dtype.names
+    packed = np.dtype([(n, "<" + data.dtype[n].str.lstrip("<>|=")) for n in names])
+    types = np.array([_TYPE_CODE[packed[n].str.lstrip("<>|=")] for n in names], np.int32)
+    offsets = np.array([packed.fields[n][1] for n in names], np.int32)
+    chunk = 1 << 15
+    out = ctypes.create_string_buffer(chunk * len(names) * 40)
+    for s in range(0, len(data), chunk):
+        rec = np.ascontiguousarray(data[s:s + chunk].astype(packed))
+        n = L.gsl_ply_format_ascii(rec.ctypes.data, len(rec), packed.itemsize, len(names), types.ctypes.data,
+                                   offsets.ctypes.data, out, len(out), 0)
+        if n < 0:
+            raise RuntimeError(L.gsl_last_error().decode())
+        f.write(memoryview(out)[:n])
+    return True
 
 
 def describe_with_label(vertex: np.ndarray, labels, name="label") -> np.ndarray:

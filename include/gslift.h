@@ -192,6 +192,18 @@ int gsl_kmeans_screen_selftest(const float *data, int64_t N, int D, const float 
  * device float32 [8][3] the host fills with COLORS (km:8), divided by 255.0 or not. */
 int gsl_recolor(const int32_t *labels, int64_t N, const float *palette, float *colors, void *stream);
 
+/*
+ * Host-side helper (no device work): ASCII body of a labelled PLY as plyfile writes it with
+ * text=True (km:190-193): every field through "%.18g" of its float64 value, one space between
+ * fields, one vertex per line.  `records` = n_rows packed little-endian records of record_size
+ * bytes; types[f] in {0:int8 1:uint8 2:int16 3:uint16 4:int32 5:uint32 6:float32 7:float64},
+ * offsets[f] = byte offset of field f.  Formats on n_threads host threads (0 = all).  Returns the
+ * number of bytes written to `out` (40 bytes per field always suffice) or a negative GSL_E* code.
+ */
+int64_t gsl_ply_format_ascii(const void *records, int64_t n_rows, int record_size, int n_fields,
+                             const int *types, const int *offsets, char *out, int64_t out_cap,
+                             int n_threads);
+
 #ifdef __cplusplus
 }
 #endif
