@@ -37,7 +37,8 @@ SIGNATURES = {
     "gsl_version": (_i32, []),
     "gsl_last_error": (ctypes.c_char_p, []),
     "gsl_device_count": (_i32, []),
-    "gsl_pack_labels": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
+    "gsl_packed_map_bytes": (_i64, [_i32, _i32]),
+    "gsl_pack_labels": (_i32, [_vp, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _vp]),
     "gsl_label_range": (_i32, [_vp, _i64, _vp, _vp]),
     "gsl_lift_workspace_bytes": (_sz, [_i64, _i32]),
     "gsl_lift_votes": (_i32, [_vp, _i64, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _dbl, _i32, _vp, _sz, _vp]),
@@ -80,8 +81,8 @@ def lib() -> ctypes.CDLL:
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        if L.gsl_version() != 1:
-            raise ImportError(f"libgslift ABI {L.gsl_version()} != 1; rebuild")
+        if L.gsl_version() != 2:
+            raise ImportError(f"libgslift ABI {L.gsl_version()} != 2; rebuild")
         _lib = L
     return _lib
 

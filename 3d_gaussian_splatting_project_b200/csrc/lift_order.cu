@@ -1,26 +1,29 @@
 // Spatial ordering and per-tile frustum culling for the lifting kernels, sm_100a.
 //
 // The vote of a Gaussian depends only on its own position, so the order in which Gaussians are
-// processed is free.  Processing them in a spatially coherent order makes every 256-Gaussian
-// tile of the gather kernel a small box in space, and then a whole (tile, view) can be proven
-// invisible -- behind the camera or outside the image for every point of the box -- with a few
-// interval evaluations, and skipped.  On the reference's own cameras (bundled cameras.json)
-// only ~13 % of (Gaussian, view) pairs are visible, so this removes most of the work; on the
-// synthetic look-at scenes it removes the ~25 % that is invisible.  Labels are unaffected: the
-// gather kernel still evaluates the reference's exact test for every pair it does not skip, and
-// the cull is conservative (margins ten times its own float32 rounding error, never the other way).
+// processed is free.  Processing them in Morton order makes (i) the 32 Gaussians of a warp
+// project into a small 2-D patch of every view, so that a gather request touches a few lines
+// of the tiled label map instead of 32, and (ii) every 256-Gaussian tile of the gather kernel a
+// small box in space, so that a whole (tile, view) can be proven invisible -- behind the camera
+// or outside the image for every point of the box -- with a few interval evaluations, and
+// skipped.  On the reference's own cameras (bundled cameras.json) only ~13 % of
+// (Gaussian, view) pairs are visible, so culling removes most of the work; on the synthetic
+// look-at scenes it removes the ~25 % that is invisible.  Labels are unaffected: the gather
+// kernel still evaluates the reference's exact test for every pair it does not skip, and the
+// cull is conservative (margins ten times its own float32 rounding error, never the other way).
 //
-//   order_bbox_kernel     min/max of the finite coordinates (ordered-uint atomics)
-//   order_cell_kernel     16^3 grid over the box, cell id = 12-bit Morton code (non-finite
-//                         positions go to an extra last cell); per-CTA shared-memory histogram
-//                         of a 16 K-row chunk, flushed with one global atomic per occupied cell
-//   order_scan_kernel     exclusive scan of the 4097 counts (one CTA)
-//   order_scatter_kernel  counting-sort scatter, same chunks: a CTA reserves a range per cell
-//                         with one global atomic and ranks its rows inside it in shared memory.
-//                         The order inside a cell depends on atomic arrival; results do not.
+//   order_stats_kernel    min/max (ordered-uint atomics) and first two moments (float64
+//                         atomics, one per CTA) of the finite coordinates
+//   order_key_kernel      256^3 grid over [mean - 4 sigma, mean + 4 sigma] clipped to the
+//                         bounding box (outliers clamp to the border cells), key = 24-bit Morton
+//                         code; non-finite positions take the last key
+//   sort_cells            (key, row) pairs by key (lift_sort.cu)
+//   order_permute_kernel  pos_sorted[i] = pos[perm[i]]
 //   order_tilebox_kernel  bounding box (+ non-finite flag) of each run of 256 sorted Gaussians
 //   order_planes_kernel   per view, the five half-spaces of the visibility test as linear forms
 //   order_cull_kernel     one bit per (tile, view), 16 views to a mask word, all views in one launch
+// The order inside a cell follows the input order (the sort is stable), so the whole ordering is
+// deterministic.
 #include "common.cuh"
 #include "lift_internal.cuh"
 
@@ -36,135 +39,118 @@ __device__ __forceinline__ float dec_f32(unsigned e)
     return __uint_as_float((e & 0x80000000u) ? (e & 0x7fffffffu) : ~e);
 }
 
+// stats layout (all 8-byte slots): u[0..2] min xyz, u[3..5] max xyz (encoded float32 in the low
+// word), d[6..8] sum, d[9..11] sum of squares, d[12] count of finite rows, then the derived grid:
+// f32 lo[3], inv[3] at byte 128.
+constexpr int kStatsBytes = 256;
+
 __global__ void __launch_bounds__(256)
-order_bbox_kernel(const float *__restrict__ pos, int64_t N, unsigned *__restrict__ bbox)
+order_stats_kernel(const float *__restrict__ pos, int64_t N, unsigned long long *__restrict__ stats)
 {
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    double s1[3] = {0.0, 0.0, 0.0}, s2[3] = {0.0, 0.0, 0.0}, cnt = 0.0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+        const float v[3] = {pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]};
+        if (fabsf(v[0]) < INFINITY && fabsf(v[1]) < INFINITY && fabsf(v[2]) < INFINITY) {
+            cnt += 1.0;
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            const float v = pos[3 * i + a];
-            if (fabsf(v) < INFINITY) { lo[a] = fminf(lo[a], v); hi[a] = fmaxf(hi[a], v); }
+            for (int a = 0; a < 3; ++a) {
+                lo[a] = fminf(lo[a], v[a]); hi[a] = fmaxf(hi[a], v[a]);
+                s1[a] += (double)v[a]; s2[a] += (double)v[a] * (double)v[a];
+            }
         }
     }
-    __shared__ float red[6][8];
+    __shared__ float redf[6][8];
+    __shared__ double redd[7][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         for (int o = 16; o; o >>= 1) {
             lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
             hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+            s1[a] += __shfl_xor_sync(0xffffffffu, s1[a], o);
+            s2[a] += __shfl_xor_sync(0xffffffffu, s2[a], o);
         }
-        if ((threadIdx.x & 31) == 0) { red[a][threadIdx.x >> 5] = lo[a]; red[3 + a][threadIdx.x >> 5] = hi[a]; }
+        if (lane == 0) { redf[a][warp] = lo[a]; redf[3 + a][warp] = hi[a]; redd[a][warp] = s1[a]; redd[3 + a][warp] = s2[a]; }
     }
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) redd[6][warp] = cnt;
     __syncthreads();
     if (threadIdx.x < 6) {                       // one atomic per CTA and bound
-        float v = red[threadIdx.x][0];
-        for (int w = 1; w < 8; ++w) v = threadIdx.x < 3 ? fminf(v, red[threadIdx.x][w]) : fmaxf(v, red[threadIdx.x][w]);
-        if (threadIdx.x < 3) atomicMin(bbox + threadIdx.x, enc_f32(v));
-        else atomicMax(bbox + threadIdx.x, enc_f32(v));
+        float v = redf[threadIdx.x][0];
+        for (int w = 1; w < 8; ++w) v = threadIdx.x < 3 ? fminf(v, redf[threadIdx.x][w]) : fmaxf(v, redf[threadIdx.x][w]);
+        unsigned *slot = reinterpret_cast<unsigned *>(stats + threadIdx.x);
+        if (threadIdx.x < 3) atomicMin(slot, enc_f32(v));
+        else atomicMax(slot, enc_f32(v));
+    } else if (threadIdx.x >= 32 && threadIdx.x < 39) {
+        const int j = threadIdx.x - 32;
+        double v = 0.0;
+        for (int w = 0; w < 8; ++w) v += redd[j][w];
+        atomicAdd(reinterpret_cast<double *>(stats + 6 + j), v);
     }
 }
 
-__device__ __forceinline__ unsigned spread4(unsigned v)      // 4 bits -> every third bit
+// Grid of the ordering: per axis [max(min, mean - 4 sigma), min(max, mean + 4 sigma)] in 256 cells.
+// Only the quality of the ordering depends on it, never a result.
+__global__ void order_grid_kernel(unsigned long long *__restrict__ stats)
 {
-    return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4) | ((v & 8u) << 6);
+    const int a = threadIdx.x;
+    if (a >= 3) return;
+    const double *d = reinterpret_cast<const double *>(stats);
+    float *grid = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(stats) + 128);
+    const double n = d[12];
+    float lo = dec_f32((unsigned)stats[a]), hi = dec_f32((unsigned)stats[3 + a]);
+    if (n > 0.0) {
+        const double mean = d[6 + a] / n;
+        const double var = fmax(d[9 + a] / n - mean * mean, 0.0);
+        const double sd = sqrt(var);
+        if (mean - 4.0 * sd > (double)lo) lo = (float)(mean - 4.0 * sd);
+        if (mean + 4.0 * sd < (double)hi) hi = (float)(mean + 4.0 * sd);
+    }
+    const float ext = hi - lo;
+    grid[a] = lo;
+    grid[3 + a] = (ext > 0.f && ext < INFINITY) ? 256.f / ext : 0.f;
 }
 
-__device__ __forceinline__ unsigned cell_of(const float *__restrict__ p, const float (&lo)[3], const float (&inv)[3])
+__device__ __forceinline__ unsigned spread8(unsigned v)      // 8 bits -> every third bit
 {
+    v = (v | (v << 16)) & 0x030000FFu;
+    v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+
+__global__ void __launch_bounds__(256)
+order_key_kernel(const float *__restrict__ pos, int64_t N, const unsigned long long *__restrict__ stats,
+                 uint32_t *__restrict__ keys, int32_t *__restrict__ idx)
+{
+    const float *grid = reinterpret_cast<const float *>(reinterpret_cast<const unsigned char *>(stats) + 128);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
     unsigned q[3];
     bool finite = true;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        const float v = p[a];
+        const float v = pos[3 * i + a];
         finite = finite && (fabsf(v) < INFINITY);
-        q[a] = (unsigned)min(max((int)((v - lo[a]) * inv[a]), 0), 15);
+        const float c = fminf(fmaxf((v - grid[a]) * grid[3 + a], 0.f), 255.f);     // NaN -> 0
+        q[a] = (unsigned)(int)c;
     }
-    return finite ? (spread4(q[0]) | (spread4(q[1]) << 1) | (spread4(q[2]) << 2)) : (unsigned)kOrderCells;
+    keys[i] = finite ? (spread8(q[0]) | (spread8(q[1]) << 1) | (spread8(q[2]) << 2)) : 0x00ffffffu;
+    idx[i] = (int32_t)i;
 }
 
-__device__ __forceinline__ void load_grid(const unsigned *__restrict__ bbox, float (&lo)[3], float (&inv)[3])
+__global__ void __launch_bounds__(256)
+order_permute_kernel(const float *__restrict__ pos, int64_t N, const int32_t *__restrict__ perm, float *__restrict__ pos_sorted)
 {
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        lo[a] = dec_f32(bbox[a]);
-        const float ext = dec_f32(bbox[3 + a]) - lo[a];
-        inv[a] = ext > 0.f && ext < INFINITY ? 16.f / ext : 0.f;
-    }
-}
-
-constexpr int kOrderChunk = 16384;     // rows per CTA in the cell / scatter kernels
-
-__global__ void __launch_bounds__(512)
-order_cell_kernel(const float *__restrict__ pos, int64_t N, const unsigned *__restrict__ bbox,
-                  uint16_t *__restrict__ cell, unsigned *__restrict__ hist)
-{
-    __shared__ unsigned local[kOrderCells + 1];
-    for (int i = threadIdx.x; i <= kOrderCells; i += blockDim.x) local[i] = 0u;
-    float lo[3], inv[3];
-    load_grid(bbox, lo, inv);
-    __syncthreads();
-    const int64_t r0 = (int64_t)blockIdx.x * kOrderChunk;
-    const int64_t r1 = min(r0 + kOrderChunk, N);
-    for (int64_t i = r0 + threadIdx.x; i < r1; i += blockDim.x) {
-        const unsigned c = cell_of(pos + 3 * i, lo, inv);
-        cell[i] = (uint16_t)c;
-        atomicAdd(local + c, 1u);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i <= kOrderCells; i += blockDim.x)
-        if (local[i]) atomicAdd(hist + i, local[i]);
-}
-
-// One CTA of 1024 threads; hist[0 .. kOrderCells] -> exclusive offsets in place.
-__global__ void __launch_bounds__(1024)
-order_scan_kernel(unsigned *__restrict__ hist)
-{
-    __shared__ unsigned part[1024];
-    constexpr int n = kOrderCells + 1;
-    constexpr int seg = (n + 1023) / 1024;
-    const int t = threadIdx.x;
-    const int lo = min(t * seg, n), hi = min(lo + seg, n);
-    unsigned s = 0;
-    for (int i = lo; i < hi; ++i) s += hist[i];
-    part[t] = s;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {            // Hillis-Steele inclusive scan
-        const unsigned v = t >= o ? part[t - o] : 0u;
-        __syncthreads();
-        part[t] += v;
-        __syncthreads();
-    }
-    unsigned run = part[t] - s;
-    for (int i = lo; i < hi; ++i) {
-        const unsigned c = hist[i];
-        hist[i] = run;
-        run += c;
-    }
-}
-
-__global__ void __launch_bounds__(512)
-order_scatter_kernel(const float *__restrict__ pos, int64_t N, const uint16_t *__restrict__ cell,
-                     unsigned *__restrict__ cursor, float *__restrict__ pos_sorted, int32_t *__restrict__ perm)
-{
-    __shared__ unsigned local[kOrderCells + 1];     // count of this chunk per cell, then its reserved base
-    for (int i = threadIdx.x; i <= kOrderCells; i += blockDim.x) local[i] = 0u;
-    __syncthreads();
-    const int64_t r0 = (int64_t)blockIdx.x * kOrderChunk;
-    const int64_t r1 = min(r0 + kOrderChunk, N);
-    for (int64_t i = r0 + threadIdx.x; i < r1; i += blockDim.x) atomicAdd(local + cell[i], 1u);
-    __syncthreads();
-    for (int i = threadIdx.x; i <= kOrderCells; i += blockDim.x)
-        if (local[i]) local[i] = atomicAdd(cursor + i, local[i]);      // reserve [base, base + count)
-    __syncthreads();
-    for (int64_t i = r0 + threadIdx.x; i < r1; i += blockDim.x) {
-        const unsigned dst = atomicAdd(local + cell[i], 1u);
-        pos_sorted[3 * (int64_t)dst + 0] = pos[3 * i + 0];
-        pos_sorted[3 * (int64_t)dst + 1] = pos[3 * i + 1];
-        pos_sorted[3 * (int64_t)dst + 2] = pos[3 * i + 2];
-        perm[dst] = (int32_t)i;
-    }
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int64_t s = perm[i];
+    pos_sorted[3 * i + 0] = pos[3 * s + 0];
+    pos_sorted[3 * i + 1] = pos[3 * s + 1];
+    pos_sorted[3 * i + 2] = pos[3 * s + 2];
 }
 
 // One warp per tile of kSheetTile sorted Gaussians: box[tile] = {lo xyz, hi xyz, nonfinite, 0}.
@@ -300,9 +286,12 @@ OrderWs order_layout(int64_t N, int V)
     o.sheet = take((size_t)((V + 3) / 4) * (size_t)n_pad * sizeof(uint32_t));
     o.pos_sorted = take((size_t)n_pad * 3 * sizeof(float));
     o.perm = take((size_t)n_pad * sizeof(int32_t));
-    o.cell = take((size_t)n_pad * sizeof(uint16_t));
-    o.hist = take((size_t)(kOrderCells + 1) * sizeof(unsigned));
-    o.bbox = take(8 * sizeof(unsigned));
+    o.keys = take((size_t)n_pad * sizeof(uint32_t));
+    o.keys_sorted = take((size_t)n_pad * sizeof(uint32_t));
+    o.idx = take((size_t)n_pad * sizeof(int32_t));
+    o.sort_temp_bytes = sort_temp_capacity(N);
+    o.sort_temp = take(o.sort_temp_bytes);
+    o.stats = take(kStatsBytes);
     o.tilebox = take((size_t)n_tiles * 8 * sizeof(float));
     o.masks = take((size_t)n_tiles * (size_t)n_words16 * sizeof(uint16_t));
     o.views = take((size_t)(V > 0 ? V : 1) * sizeof(GslView));
@@ -311,16 +300,17 @@ OrderWs order_layout(int64_t N, int V)
     return o;
 }
 
-// Sort positions into cells, box the tiles, and decide per (tile, view) whether the view must be
-// swept.  All launches on `st`; `views` is the caller's host table.
+// Sort positions into Morton order, box the tiles, and decide per (tile, view) whether the view
+// must be swept.  All launches on `st`; `views` is the caller's host table.
 int order_gaussians(const float *pos, int64_t N, const GslView *views, int V, unsigned char *base,
                     const OrderWs &L, cudaStream_t st)
 {
     float *pos_sorted = reinterpret_cast<float *>(base + L.pos_sorted);
     int32_t *perm = reinterpret_cast<int32_t *>(base + L.perm);
-    uint16_t *cell = reinterpret_cast<uint16_t *>(base + L.cell);
-    unsigned *hist = reinterpret_cast<unsigned *>(base + L.hist);
-    unsigned *bbox = reinterpret_cast<unsigned *>(base + L.bbox);
+    uint32_t *keys = reinterpret_cast<uint32_t *>(base + L.keys);
+    uint32_t *keys_sorted = reinterpret_cast<uint32_t *>(base + L.keys_sorted);
+    int32_t *idx = reinterpret_cast<int32_t *>(base + L.idx);
+    unsigned long long *stats = reinterpret_cast<unsigned long long *>(base + L.stats);
     float *tilebox = reinterpret_cast<float *>(base + L.tilebox);
     uint16_t *masks = reinterpret_cast<uint16_t *>(base + L.masks);
     GslView *d_views = reinterpret_cast<GslView *>(base + L.views);
@@ -328,23 +318,22 @@ int order_gaussians(const float *pos, int64_t N, const GslView *views, int V, un
     const int64_t n_tiles = (N + kSheetTile - 1) / kSheetTile;
     const int n_words16 = (V + 15) / 16;
 
-    // pageable source: the runtime stages the table before returning
-    GSL_CUDA_TRY(cudaMemcpyAsync(d_views, views, sizeof(GslView) * (size_t)V, cudaMemcpyHostToDevice, st));
-    GSL_CUDA_TRY(cudaMemsetAsync(bbox, 0xff, 3 * sizeof(unsigned), st));
-    GSL_CUDA_TRY(cudaMemsetAsync(bbox + 3, 0x00, 3 * sizeof(unsigned), st));
-    GSL_CUDA_TRY(cudaMemsetAsync(hist, 0, (size_t)(kOrderCells + 1) * sizeof(unsigned), st));
+    (void)views;                                   // already in the workspace (gsl_lift_prepare)
+    GSL_CUDA_TRY(cudaMemsetAsync(stats, 0xff, 3 * 8, st));
+    GSL_CUDA_TRY(cudaMemsetAsync(stats + 3, 0x00, kStatsBytes - 3 * 8, st));
     int64_t blocks = (N + 256 * 8 - 1) / (256 * 8);
     const int64_t cap = (int64_t)sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    order_bbox_kernel<<<(unsigned)blocks, 256, 0, st>>>(pos, N, bbox);
-    GSL_LAUNCH_CHECK("order_bbox_kernel");
-    const unsigned chunks = (unsigned)((N + kOrderChunk - 1) / kOrderChunk);
-    order_cell_kernel<<<chunks, 512, 0, st>>>(pos, N, bbox, cell, hist);
-    GSL_LAUNCH_CHECK("order_cell_kernel");
-    order_scan_kernel<<<1, 1024, 0, st>>>(hist);
-    GSL_LAUNCH_CHECK("order_scan_kernel");
-    order_scatter_kernel<<<chunks, 512, 0, st>>>(pos, N, cell, hist, pos_sorted, perm);
-    GSL_LAUNCH_CHECK("order_scatter_kernel");
+    order_stats_kernel<<<(unsigned)blocks, 256, 0, st>>>(pos, N, stats);
+    GSL_LAUNCH_CHECK("order_stats_kernel");
+    order_grid_kernel<<<1, 32, 0, st>>>(stats);
+    GSL_LAUNCH_CHECK("order_grid_kernel");
+    const unsigned rows_grid = (unsigned)((N + 255) / 256);
+    order_key_kernel<<<rows_grid, 256, 0, st>>>(pos, N, stats, keys, idx);
+    GSL_LAUNCH_CHECK("order_key_kernel");
+    if (int rc = sort_cells(keys, keys_sorted, idx, perm, N, base + L.sort_temp, L.sort_temp_bytes, st)) return rc;
+    order_permute_kernel<<<rows_grid, 256, 0, st>>>(pos, N, perm, pos_sorted);
+    GSL_LAUNCH_CHECK("order_permute_kernel");
     order_tilebox_kernel<<<(unsigned)((n_tiles + 7) / 8), 256, 0, st>>>(pos_sorted, N, n_tiles, tilebox);
     GSL_LAUNCH_CHECK("order_tilebox_kernel");
     order_planes_kernel<<<(V + 127) / 128, 128, 0, st>>>(d_views, V, planes);

@@ -125,8 +125,9 @@ def _stage_maps(seg_maps, shapes, device, label_min, n_classes):
     world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank() if world > 1 else 0
     sizes = [h * w for h, w in shapes]
-    starts = np.concatenate(([0], np.cumsum(sizes))).astype(np.int64)
-    total = int(starts[-1])
+    starts = np.concatenate(([0], np.cumsum(sizes))).astype(np.int64)     # pixels, row-major staging
+    pstarts = ops.packed_offsets(shapes)                                   # bytes, packed layout
+    total = int(pstarts[-1])
     V = len(seg_maps)
     per, extra = divmod(V, world)
     cuts = [r * per + min(r, extra) for r in range(world + 1)]
@@ -146,17 +147,17 @@ def _stage_maps(seg_maps, shapes, device, label_min, n_classes):
             mm = torch.tensor([lo, -hi], dtype=torch.int64, device=device)
             dist.all_reduce(mm, op=dist.ReduceOp.MIN)
             lo, hi = int(mm[0].item()), -int(mm[1].item())
-        if total == 0:
+        if int(starts[-1]) == 0:
             lo, hi = ops.DEFAULT_LABEL_MIN, ops.DEFAULT_LABEL_MIN
         if hi - lo + 1 > ops.DEFAULT_N_CLASSES:
             raise ValueError(f"label maps span {hi - lo + 1} values; at most {ops.DEFAULT_N_CLASSES} are supported")
         label_min, n_classes = lo, hi - lo + 1
     packed = torch.empty(total, dtype=torch.uint8, device=device)
     if mine:
-        ops.pack_labels(staged, label_min, n_classes, out=packed[int(starts[v_lo]):int(starts[v_hi])])
+        ops.pack_labels(staged, shapes[v_lo:v_hi], label_min, n_classes, out=packed[int(pstarts[v_lo]):int(pstarts[v_hi])])
     if world > 1:
         for r in range(world):
-            lo_px, hi_px = int(starts[cuts[r]]), int(starts[cuts[r + 1]])
+            lo_px, hi_px = int(pstarts[cuts[r]]), int(pstarts[cuts[r + 1]])
             if hi_px > lo_px:
                 dist.broadcast(packed[lo_px:hi_px], src=r)
     return packed, label_min, n_classes
@@ -175,8 +176,9 @@ def _lift_pipelined(pos, views, seg_maps, shapes, device):
     L = lib()
     N, V = pos.shape[0], len(views)
     sizes = [h * w for h, w in shapes]
-    starts = np.concatenate(([0], np.cumsum(sizes))).astype(np.int64)
-    packed = torch.empty(int(starts[-1]), dtype=torch.uint8, device=device)
+    starts = np.concatenate(([0], np.cumsum(sizes))).astype(np.int64)     # pixels, row-major staging
+    pstarts = ops.packed_offsets(shapes)                                   # bytes, packed layout
+    packed = torch.empty(int(pstarts[-1]), dtype=torch.uint8, device=device)
     ws = ops._ws.get(device, L.gsl_lift_workspace_bytes(N, V))
     main = torch.cuda.current_stream(device)
     key = (device.type, device.index)
@@ -208,8 +210,14 @@ def _lift_pipelined(pos, views, seg_maps, shapes, device):
                 ready.record(copy)
             main.wait_event(ready)
             check(L.gsl_label_range(buf.data_ptr(), off, minmax.data_ptr(), main.cuda_stream))
-            check(L.gsl_pack_labels(buf.data_ptr(), packed.data_ptr() + int(starts[v0]), off, -1, 255,
-                                    err.data_ptr(), main.cuda_stream))
+            v = v0
+            while v < v1:                                # one pack launch per run of equal shapes
+                n = 1
+                while v + n < v1 and shapes[v + n] == shapes[v]:
+                    n += 1
+                check(L.gsl_pack_labels(buf.data_ptr() + 4 * int(starts[v] - starts[v0]), n, shapes[v][1], shapes[v][0],
+                                        packed.data_ptr() + int(pstarts[v]), -1, 255, err.data_ptr(), main.cuda_stream))
+                v += n
             slot_free[ci % 2] = torch.cuda.Event()
             slot_free[ci % 2].record(main)
             check(L.gsl_lift_gather_range(pos.data_ptr(), N, vptr, V, v0, v1, packed.data_ptr(), None, 0.0, 0,
@@ -240,7 +248,7 @@ def lift_labels(positions, cameras, seg_maps, image_sizes=None, device=None, wan
     import torch.distributed as dist
     single = not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
     if (single and not want_near and label_min is None and n_classes is None and len(views) and pos.shape[0]
-            and all(int(np.prod(sh)) % 4 == 0 for sh in shapes)):
+            and all(len(sh) == 2 for sh in shapes)):
         fast = _lift_pipelined(pos, views, seg_maps, shapes, device)
         if fast is not None:
             return _to_host(fast)

@@ -46,16 +46,31 @@ _ws = _Workspace()
 # --------------------------------------------------------------------------------------
 # lifting
 # --------------------------------------------------------------------------------------
+def packed_map_bytes(seg_h: int, seg_w: int) -> int:
+    """Bytes of one packed (tiled) label map of seg_h x seg_w pixels (include/gslift.h)."""
+    tiles_x = (int(seg_w) + 15) // 16 + 2
+    tiles_y = (int(seg_h) + 7) // 8 + 2
+    return tiles_x * tiles_y * 128
+
+
+def packed_offsets(map_shapes) -> np.ndarray:
+    """Byte offset of every view's packed map when the maps are laid out back to back, plus
+    the total as the last entry (int64 [V + 1])."""
+    sizes = [packed_map_bytes(h, w) for h, w in map_shapes]
+    return np.concatenate(([0], np.cumsum(sizes, dtype=np.int64))).astype(np.int64)
+
+
 def make_views(cameras, map_shapes, image_sizes=None) -> np.ndarray:
     """Camera dicts (cameras.json schema, dls:54-63) -> GslView table.
 
     map_shapes[v] = (seg_h, seg_w) of view v's segmentation map (dls:267);
     image_sizes[v] = (orig_w, orig_h) of the opened image (dls:263), default the map size.
     `t` is evaluated with the reference's own expression `-R @ p` (dls:66) so it carries the
-    same rounding the reference would see on this host.  Maps are laid out back to back.
+    same rounding the reference would see on this host.  Packed maps are laid out back to back
+    (packed_offsets).
     """
     views = np.zeros(len(cameras), VIEW_DTYPE)
-    off = 0
+    offs = packed_offsets([tuple(int(s) for s in sh) for sh in map_shapes]) if len(cameras) else np.zeros(1, np.int64)
     for v, cam in enumerate(cameras):
         R = np.array(cam["rotation"])
         p = np.array(cam["position"])
@@ -69,25 +84,51 @@ def make_views(cameras, map_shapes, image_sizes=None) -> np.ndarray:
         rec["width"], rec["height"] = cam["width"], cam["height"]
         rec["scale_x"], rec["scale_y"] = seg_w / ow, seg_h / oh
         rec["seg_w"], rec["seg_h"] = seg_w, seg_h
-        rec["map_offset"] = off
-        off += seg_h * seg_w
+        rec["map_offset"] = int(offs[v])
     return views
 
 
-def pack_labels(maps: torch.Tensor, label_min: int = DEFAULT_LABEL_MIN,
+def pack_labels(maps: torch.Tensor, shapes=None, label_min: int = DEFAULT_LABEL_MIN,
                 n_classes: int = DEFAULT_N_CLASSES, out: torch.Tensor | None = None,
                 check_range: bool = True) -> torch.Tensor:
-    """int32 label maps (any shape, device) -> uint8 codes `label - label_min + 1`."""
+    """int32 label maps (device) -> uint8 codes `label - label_min + 1` in the library's tiled
+    layout, maps back to back (packed_offsets).
+
+    maps    [n, h, w] or [h, w] tensor, or a flat tensor together with `shapes` = [(h, w), ...]
+            listing the row-major maps it holds back to back.
+    """
     _require_cuda(maps, "maps")
     if maps.dtype != torch.int32:
         raise TypeError("maps must be int32 (what segment_image returns, dls:158)")
-    n_px = maps.numel()
+    if shapes is None:
+        if maps.dim() == 2:
+            shapes = [tuple(maps.shape)]
+        elif maps.dim() == 3:
+            shapes = [tuple(maps.shape[1:])] * maps.shape[0]
+        else:
+            raise ValueError("flat maps need shapes=[(h, w), ...]")
+    shapes = [(int(h), int(w)) for h, w in shapes]
+    if sum(h * w for h, w in shapes) != maps.numel():
+        raise ValueError("shapes do not add up to maps.numel()")
+    offs = packed_offsets(shapes)
     if out is None:
-        out = torch.empty(n_px, dtype=torch.uint8, device=maps.device)
+        out = torch.empty(int(offs[-1]), dtype=torch.uint8, device=maps.device)
+    elif out.numel() < int(offs[-1]) or out.dtype != torch.uint8:
+        raise ValueError(f"out must be uint8 with at least {int(offs[-1])} elements")
     err = torch.zeros(1, dtype=torch.int32, device=maps.device)
+    flat = maps.reshape(-1)
+    L = lib()
     with torch.cuda.device(maps.device):
-        check(lib().gsl_pack_labels(maps.data_ptr(), out.data_ptr(), n_px, int(label_min),
-                                    int(n_classes), err.data_ptr(), _stream()))
+        v, src = 0, 0
+        while v < len(shapes):                       # one launch per run of equal shapes
+            n = 1
+            while v + n < len(shapes) and shapes[v + n] == shapes[v]:
+                n += 1
+            h, w = shapes[v]
+            check(L.gsl_pack_labels(flat.data_ptr() + 4 * src, n, w, h, out.data_ptr() + int(offs[v]),
+                                    int(label_min), int(n_classes), err.data_ptr(), _stream()))
+            src += n * h * w
+            v += n
     if check_range and int(err.item()) != 0:
         raise ValueError(f"label map value outside [{label_min}, {label_min + n_classes})")
     return out
@@ -121,9 +162,9 @@ def lift_votes(pos: torch.Tensor, views: np.ndarray, packed: torch.Tensor,
     V = len(views)
     if V:
         _require_cuda(packed, "packed")
-        need = int((views["map_offset"] + views["seg_w"].astype(np.int64) * views["seg_h"]).max())
+        need = max(int(r["map_offset"]) + packed_map_bytes(int(r["seg_h"]), int(r["seg_w"])) for r in views)
         if packed.numel() < need:
-            raise ValueError(f"packed holds {packed.numel()} px, views address {need}")
+            raise ValueError(f"packed holds {packed.numel()} bytes, views address {need}")
     N = pos.shape[0]
     labels = out if out is not None else torch.empty(N, dtype=torch.int32, device=pos.device)
     near = torch.empty(N, dtype=torch.uint8, device=pos.device) if want_near else None

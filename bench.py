@@ -243,19 +243,20 @@ def run_native(a):
 
     # ---- resident inputs: positions slice + packed maps (staged 8 views at a time)
     d_pos = torch.from_numpy(pos[lo:hi]).to(dev)
-    packed = torch.empty(V * H * W, dtype=torch.uint8, device=dev)
+    PB = ops.packed_map_bytes(H, W)                # tiled layout: 16 x 8-pixel tiles + a ring of zero tiles
+    packed = torch.empty(V * PB, dtype=torch.uint8, device=dev)
     for v0 in range(0, V, 8):
         v1 = min(v0 + 8, V)
         chunk = maps_pinned[v0:v1].to(dev, non_blocking=True)
-        ops.pack_labels(chunk, -1, 151, out=packed[v0 * H * W:v1 * H * W], check_range=False)
+        ops.pack_labels(chunk, label_min=-1, n_classes=151, out=packed[v0 * PB:v1 * PB], check_range=False)
     # staging cost of the pack pre-pass (5 bytes per pixel), timed on a resident 8-view chunk
     pack_ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     n_chunk = min(8, V)
-    scratch = torch.empty(n_chunk * H * W, dtype=torch.uint8, device=dev)
+    scratch = torch.empty(n_chunk * PB, dtype=torch.uint8, device=dev)
     for i in range(6):
         if i == 1:
             pack_ev[0].record()
-        ops.pack_labels(chunk[:n_chunk], -1, 151, out=scratch, check_range=False)
+        ops.pack_labels(chunk[:n_chunk], label_min=-1, n_classes=151, out=scratch, check_range=False)
     pack_ev[1].record()
     torch.cuda.synchronize()
     pack_ms = pack_ev[0].elapsed_time(pack_ev[1]) / 5 * (V / n_chunk)
@@ -284,8 +285,8 @@ def run_native(a):
     total_ms = sharding.barrier_max_ms(total_ms, dev)
     ms_per_step = total_ms / a.steps
     value = a.gaussians * V / (ms_per_step * 1e-3)
-    # kernels of one lifting step: 7 ordering/culling kernels, one gather per 16-view window, 1 majority
-    n_lift_launches = 7 + (V + 15) // 16 + 1
+    # kernels of one lifting step: 12 ordering/culling kernels (5 of them the radix sort), one gather per 16-view window, 1 majority
+    n_lift_launches = 12 + (V + 15) // 16 + 1
     label_hist = torch.bincount((labels + 1).clamp(min=0).long(), minlength=152)[:3].tolist()
 
     # ---- K-means, device resident

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GSL_ABI_VERSION 1
+#define GSL_ABI_VERSION 2
 
 #define GSL_OK        0
 #define GSL_EINVAL   -1   /* bad argument (NULL pointer, negative size, V/K/D out of range) */
@@ -59,7 +59,7 @@ typedef struct GslView {
     double scale_y;    /* seg_height / orig_height                                 dls:270   */
     int32_t seg_w;     /* seg_map.shape[1]                                         dls:267   */
     int32_t seg_h;     /* seg_map.shape[0]                                                   */
-    int64_t map_offset;/* element offset of this view's [seg_h][seg_w] map in `maps`         */
+    int64_t map_offset;/* byte offset of this view's packed map (gsl_pack_labels) in `packed`*/
 } GslView;             /* 176 bytes */
 
 /* ABI version (GSL_ABI_VERSION of the built library). */
@@ -76,8 +76,18 @@ int gsl_device_count(void);
  * codes  code = label - label_min + 1  (0 is reserved for "not visible").
  * Values outside [label_min, label_min + n_classes) set *d_err (device int, caller zeroes
  * it) to 1 and are written as code 0.  n_classes <= GSL_MAX_CODES.
+ *
+ *   maps    n_maps row-major int32 maps of seg_h x seg_w, back to back (4-byte aligned; 16-byte
+ *           alignment and seg_w % 4 == 0 enable the vector path)
+ *   packed  n_maps packed maps of gsl_packed_map_bytes(seg_w, seg_h) bytes each, back to back
+ *           (16-byte aligned).  The packed layout is private to the library: 16 x 8-pixel tiles
+ *           of 128 bytes surrounded by a ring of zero tiles, so that the 32 gathers of a warp of
+ *           neighbouring Gaussians touch a few cache lines instead of one per image row.
+ * Views with different map shapes are packed by separate calls; GslView.map_offset is the byte
+ * offset of a view's packed map inside the buffer handed to gsl_lift_votes.
  */
-int gsl_pack_labels(const int32_t *maps, uint8_t *packed, int64_t n_px,
+int64_t gsl_packed_map_bytes(int seg_w, int seg_h);
+int gsl_pack_labels(const int32_t *maps, int n_maps, int seg_w, int seg_h, uint8_t *packed,
                     int label_min, int n_classes, int *d_err, void *stream);
 
 /* Device min/max of an int32 buffer into d_minmax[2] (caller initialises to INT_MAX,
@@ -89,8 +99,9 @@ size_t gsl_lift_workspace_bytes(int64_t N, int V);
 
 /*
  * The vote loop and the majority of assign_labels (dls:255-306) for precomputed maps:
- * for every Gaussian, every view in order: project (dls:43-82, float64), test z > 0 and
- * image bounds, rescale + clamp (dls:281-286), gather the code, count; then
+ * for every Gaussian, every view in order: project (dls:43-82, float64 -- evaluated in float32
+ * first and re-evaluated in float64 wherever the float32 error bound cannot prove the float64
+ * outcome), test z > 0 and image bounds, rescale + clamp (dls:281-286), gather the code, count; then
  * labels[i] = the label with the most votes, the one seen first in view order on a tie
  * (Python max() over an insertion-ordered dict, dls:303), or -1 if never visible (dls:306).
  *

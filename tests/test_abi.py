@@ -30,7 +30,7 @@ def test_library_is_built_and_exports_every_declared_symbol():
 
 def test_version_and_view_struct_size():
     native = pkg("_native")
-    assert native.lib().gsl_version() == 1
+    assert native.lib().gsl_version() == 2
     hdr = open(os.path.join(ROOT, "include", "gslift.h")).read()
     assert "176 bytes" in hdr and native.VIEW_DTYPE.itemsize == 176
 
@@ -47,7 +47,8 @@ def test_workspace_queries_are_host_only():
 def test_argument_validation_needs_no_device():
     native = pkg("_native")
     L = native.lib()
-    assert L.gsl_pack_labels(None, None, 10, -1, 255, None, None) == -1
+    assert L.gsl_pack_labels(None, 1, 8, 8, None, -1, 255, None, None) == -1
+    assert L.gsl_packed_map_bytes(1920, 1080) == 122 * 137 * 128 and L.gsl_packed_map_bytes(0, 5) == 0
     assert b"null" in L.gsl_last_error()
     assert L.gsl_lift_votes(None, -1, None, 0, None, -1, 255, None, None, 0.0, 0, None, 0, None) == -1
     assert L.gsl_kmeans_assign(None, 10, 0, None, 4, None, None, 0, None) == -1

@@ -16,7 +16,7 @@ def test_abi_error_codes_on_device():
     cams = scene.lookat_cameras(3, width=64, height=48, seed=1)
     views = ops.make_views(cams, [(48, 64)] * 3)
     pos = torch.zeros(10, 3, device=DEV)
-    packed = torch.zeros(3 * 48 * 64, dtype=torch.uint8, device=DEV)
+    packed = torch.zeros(3 * ops.packed_map_bytes(48, 64), dtype=torch.uint8, device=DEV)
     labels = torch.empty(10, dtype=torch.int32, device=DEV)
     ws = torch.empty(64, dtype=torch.uint8, device=DEV)
     rc = L.gsl_lift_votes(pos.data_ptr(), 10, views.ctypes.data, 3, packed.data_ptr(), -1, 255, labels.data_ptr(),
@@ -33,8 +33,10 @@ def test_abi_error_codes_on_device():
     assert rc == -1 and b"view 1" in L.gsl_last_error()
     maps = torch.zeros(1024 + 1, dtype=torch.int32, device=DEV)
     err = torch.zeros(1, dtype=torch.int32, device=DEV)
-    rc = L.gsl_pack_labels(maps.data_ptr() + 4, packed.data_ptr(), 1024, -1, 255, err.data_ptr(), None)
+    rc = L.gsl_pack_labels(maps.data_ptr() + 2, 1, 32, 32, packed.data_ptr(), -1, 255, err.data_ptr(), None)
     assert rc == -1 and b"aligned" in L.gsl_last_error()
+    rc = L.gsl_pack_labels(maps.data_ptr(), 1, 0, 32, packed.data_ptr(), -1, 255, err.data_ptr(), None)
+    assert rc == -1 and b"shape" in L.gsl_last_error()
     rc = L.gsl_lift_gather_range(pos.data_ptr(), 10, views.ctypes.data, 3, 8, 3, packed.data_ptr(), None, 0.0, 0,
                                  big.data_ptr(), big.numel(), None)
     assert rc == -1 and b"view range" in L.gsl_last_error()
@@ -77,7 +79,7 @@ def test_random_small_scenes_against_pure_python(oracle, seed):
     want_c, _, _ = oracle.lift_votes(pos, oracle.make_views(cams, shapes, sizes), flat)
     assert np.array_equal(want_c, want_py), "C oracle and pure-Python restatement disagree"
     views = ops.make_views(cams, shapes, sizes)
-    packed = ops.pack_labels(torch.from_numpy(flat).to(DEV))
+    packed = ops.pack_labels(torch.from_numpy(flat).to(DEV), shapes)
     got = ops.lift_votes(torch.from_numpy(pos).to(DEV), views, packed).cpu().numpy()
     assert np.array_equal(got, want_c)
 

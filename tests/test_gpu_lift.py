@@ -20,7 +20,7 @@ def gpu_lift(pos, cameras, maps_list, sizes, **kw):
     shapes = [m.shape for m in maps_list]
     views = ops.make_views(cameras, shapes, sizes)
     flat = np.concatenate([np.ascontiguousarray(m, np.int32).reshape(-1) for m in maps_list]) if maps_list else np.zeros(0, np.int32)
-    packed = ops.pack_labels(torch.from_numpy(flat).to(DEV))
+    packed = ops.pack_labels(torch.from_numpy(flat).to(DEV), shapes) if maps_list else torch.zeros(0, dtype=torch.uint8, device=DEV)
     res = ops.lift_votes(torch.from_numpy(np.ascontiguousarray(pos, np.float32)).to(DEV), views, packed, **kw)
     torch.cuda.synchronize()
     return res
@@ -176,7 +176,7 @@ def test_empty_inputs_and_label_range():
     assert out.numel() == 0
     none = ops.lift_votes(torch.from_numpy(pos).to(DEV), ops.make_views([], []), torch.zeros(0, dtype=torch.uint8, device=DEV))
     assert (none.cpu().numpy() == -1).all()            # no views: nothing visible (dls:306)
-    bad = torch.full((64,), 1000, dtype=torch.int32, device=DEV)
+    bad = torch.full((8, 8), 1000, dtype=torch.int32, device=DEV)
     with pytest.raises(ValueError):
         ops.pack_labels(bad)
     assert ops.label_range(torch.tensor([5, -3, 77], dtype=torch.int32, device=DEV)) == (-3, 77)
@@ -196,16 +196,17 @@ def test_full_size_c3_properties_and_oracle(oracle):
     cams = scene.lookat_cameras(v, width=w, height=h, seed=3)
     pos = scene.gaussian_cloud(n, 1.5, seed=3)
     views = ops.make_views(cams, [(h, w)] * v)
-    packed = torch.empty(v * h * w, dtype=torch.uint8, device=DEV)
+    pb = ops.packed_map_bytes(h, w)
+    packed = torch.empty(v * pb, dtype=torch.uint8, device=DEV)
     maps = scene.block_label_maps(v, h, w, block=32, seed=1000)
     for v0 in range(0, v, 8):                          # stage + pack 8 maps at a time
-        ops.pack_labels(torch.from_numpy(maps[v0:v0 + 8]).to(DEV), out=packed[v0 * h * w:(v0 + 8) * h * w])
+        ops.pack_labels(torch.from_numpy(maps[v0:v0 + 8]).to(DEV), out=packed[v0 * pb:(v0 + 8) * pb])
     d_pos = torch.from_numpy(pos).to(DEV)
     full = ops.lift_votes(d_pos, views, packed).cpu().numpy()
     again = ops.lift_votes(d_pos, views, packed).cpu().numpy()
     assert np.array_equal(full, again)
-    # float32 screening (opt-in) and ordering+culling (default) are execution strategies only
-    for var, val in (("GSLIFT_LIFT_SCREEN", "1"), ("GSLIFT_LIFT_ORDER", "0")):
+    # float32 screening and ordering+culling (both default) are execution strategies only
+    for var, val in (("GSLIFT_LIFT_F64", "1"), ("GSLIFT_LIFT_ORDER", "0")):
         os.environ[var] = val
         try:
             plain = ops.lift_votes(d_pos, views, packed).cpu().numpy()
