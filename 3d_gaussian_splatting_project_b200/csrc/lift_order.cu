@@ -23,7 +23,7 @@
 //   order_planes_kernel   per view, the five half-spaces of the visibility test as linear forms
 //   order_cull_kernel     one bit per (tile, view), 16 views to a mask word, all views in one launch
 // The order inside a cell follows the input order (the sort is stable), so the whole ordering is
-// deterministic.
+// deterministic.  (A 1024^3 grid with 30-bit keys was measured: one more sort pass, same gather time.)
 #include "common.cuh"
 #include "lift_internal.cuh"
 

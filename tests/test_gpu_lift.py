@@ -154,6 +154,17 @@ def test_view_window_and_chunking_do_not_change_results(oracle):
     cams, pos, maps = _scene(3000, 401, 48, 32, seed=9, block=4)
     want, _, _ = oracle.lift_votes(pos, oracle.make_views(cams, [(32, 48)] * 401), maps)
     compare(gpu_lift(pos, cams, list(maps), None).cpu().numpy(), want)
+    # 256 <= V <= 508 counts with 16-bit word-resolution keys; the 32-bit keys must agree, also on a
+    # tie-heavy scene (few labels, so equal counts with first sightings inside one sheet word are common)
+    scene = pkg("scene")
+    few = np.stack([scene.block_label_map(32, 48, 4, 0, 2, 700 + i) for i in range(401)])
+    want_few, _, _ = oracle.lift_votes(pos, oracle.make_views(cams, [(32, 48)] * 401), few)
+    compare(gpu_lift(pos, cams, list(few), None).cpu().numpy(), want_few)
+    os.environ["GSLIFT_MAJORITY_WIDE"] = "1"
+    try:
+        compare(gpu_lift(pos, cams, list(few), None).cpu().numpy(), want_few)
+    finally:
+        del os.environ["GSLIFT_MAJORITY_WIDE"]
 
 
 def test_rescaled_and_ragged_maps(oracle):
