@@ -51,6 +51,8 @@ SIGNATURES = {
     "gsl_kmeans_assign": (_i32, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _sz, _vp]),
     "gsl_kmeans_step": (_i32, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _sz, _vp]),
     "gsl_kmeans_finalize": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "gsl_kmeans_exchange_bytes": (_sz, [_i32, _i32, _i32]),
+    "gsl_kmeans_step_exchange": (_i32, [_vp, _i64, _i32, _vp, _i32, _vp, _i32, _i32, _vp, ctypes.c_uint64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gsl_kmeans_update_ordered": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gsl_kmeans_screen_selftest": (_i32, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp]),
     "gsl_ply_format_ascii": (_i64, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _i64, _i32]),

@@ -15,6 +15,7 @@
 //        and a fixed order, so results are bit-reproducible.
 //   kmeans_reduce_kernel      fixed-order sum of the per-CTA partials -> sums[K][D+1]
 //   kmeans_finalize_kernel    new = float32(sum / count) or old; shift = ||new - old||_F
+//   kmeans_exchange_kernel    reduce + push to every rank over peer memory + rank-ordered total + finalize
 //
 // Compiled with -fmad=false (the distance must not be contracted).
 #include <stdlib.h>
@@ -210,6 +211,119 @@ kmeans_finalize_kernel(const double *__restrict__ sums, const float *__restrict_
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Reduction fused with the cross-rank exchange and the update (one kernel per iteration instead of
+// reduce + NCCL all-reduce + finalize).  Every rank owns an exchange buffer that all ranks can
+// address (peer mapping over NVLink: torch symmetric memory on the Python side):
+//     [0]    done counter of the local grid          [128] flags[rank], one u64 per source rank
+//     [256]  slots[parity][source rank][n_el] float64
+//   1. every CTA sums its 32 elements over the per-CTA partials of the step kernel (same fixed
+//      grouping as kmeans_reduce_kernel) and PUSHES the result into slot[parity][my rank] of every
+//      rank's buffer -- 256-byte coalesced stores straight into peer memory;
+//   2. the last CTA to finish (device-scope ticket after a system-scope fence) publishes
+//      flag[my rank] = seq on every rank with a system-scope release store, then waits until its
+//      own flags from all ranks have reached seq (acquire loads);
+//   3. it adds the `world` slots in RANK ORDER -- the same order on every rank, so all ranks get
+//      bit-identical totals and centroids -- and forms the new centroids and the shift.
+// seq grows by one per call; slots alternate by its parity.  That is enough: a rank can only be
+// one exchange ahead of a peer (to start exchange s + 1 it needs that peer's flag for s), so
+// the data of exchange s is never overwritten before exchange s + 2, by which time every rank has
+// finished reading s.  The wait is bounded (2 s): on a time-out the shift comes back NaN.
+// ---------------------------------------------------------------------------------------
+constexpr int kMaxRanks = 16;
+constexpr size_t kXchgFlags = 128, kXchgSlots = 256;
+
+struct PeerTable {
+    unsigned char *base[kMaxRanks];
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__global__ void __launch_bounds__(256)
+kmeans_exchange_kernel(const double *__restrict__ partials, int n_parts, int n_el, PeerTable peers, int rank, int world,
+                       unsigned long long seq, const float *__restrict__ old_c, int K, int D,
+                       float *__restrict__ new_c, float *__restrict__ shift, double *__restrict__ sums)
+{
+    __shared__ double part[8][32];
+    __shared__ int s_last, s_timeout;
+    __shared__ double red[8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const size_t slot_off = kXchgSlots + ((size_t)(seq & 1ull) * world + rank) * (size_t)n_el * sizeof(double);
+    {
+        const int i = blockIdx.x * 32 + lane;
+        double s = 0.0;
+        if (i < n_el)
+            for (int p = w; p < n_parts; p += 8) s += partials[(size_t)p * n_el + i];
+        part[w][lane] = s;
+        __syncthreads();
+        if (w == 0 && i < n_el) {
+            double t = part[0][lane];
+            for (int ww = 1; ww < 8; ++ww) t += part[ww][lane];
+            for (int p = 0; p < world; ++p)                                  // push: own sums into everyone's slot[rank]
+                reinterpret_cast<double *>(peers.base[p] + slot_off)[i] = t;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    unsigned *counter = reinterpret_cast<unsigned *>(peers.base[rank]);
+    if (threadIdx.x == 0) {
+        s_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+        s_timeout = 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence_system();
+    if (threadIdx.x == 0) *counter = 0u;                                     // next call on this stream starts from zero
+    if (threadIdx.x < world) {
+        st_release_sys(reinterpret_cast<unsigned long long *>(peers.base[threadIdx.x] + kXchgFlags) + rank, seq);
+        const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(peers.base[rank] + kXchgFlags) + threadIdx.x;
+        const unsigned long long t0 = global_ns();
+        while (ld_acquire_sys(mine) < seq)
+            if (global_ns() - t0 > 2000000000ull) { s_timeout = 1; break; }
+    }
+    __syncthreads();
+    const double *slots = reinterpret_cast<const double *>(peers.base[rank] + kXchgSlots + (size_t)(seq & 1ull) * world * (size_t)n_el * sizeof(double));
+    for (int i = threadIdx.x; i < n_el; i += blockDim.x) {
+        double t = 0.0;
+        for (int p = 0; p < world; ++p) t += __ldcg(slots + (size_t)p * n_el + i);   // rank order; L2 is the coherence point
+        sums[i] = t;
+    }
+    __syncthreads();                                                         // this CTA's writes to `sums` are visible to it
+    double sq = 0.0;
+    for (int i = threadIdx.x; i < K * D; i += blockDim.x) {
+        const int k = i / D, d = i - k * D;
+        const double n = sums[k * (D + 1) + D];
+        const float o = old_c[i];
+        const float v = n > 0.0 ? (float)(sums[k * (D + 1) + d] / n) : o;    // km:126; empty cluster keeps its centroid
+        new_c[i] = v;
+        const float df = v - o;
+        sq += (double)df * (double)df;
+    }
+    for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if (lane == 0) red[w] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int ww = 0; ww < 8; ++ww) s += red[ww];
+        *shift = s_timeout ? __int_as_float(0x7fc00000) : (float)sqrt(s);
+    }
+}
+
 __global__ void __launch_bounds__(256)
 recolor_kernel(const int32_t *__restrict__ labels, int64_t N, const float *__restrict__ palette,
                float *__restrict__ colors)
@@ -330,6 +444,42 @@ extern "C" int gsl_kmeans_step(const float *data, int64_t N, int D, const float 
     if (int rc = launch_step<true>(data, N, D, centroids, K, labels, partials, grid, st)) return rc;
     kmeans_reduce_kernel<<<(n_el + 31) / 32, 256, 0, st>>>(partials, grid, n_el, sums);
     GSL_LAUNCH_CHECK("kmeans_reduce_kernel");
+    return GSL_OK;
+}
+
+extern "C" size_t gsl_kmeans_exchange_bytes(int world, int D, int K)
+{
+    if (world < 1 || world > kMaxRanks || D < 1 || K < 1) return 0;
+    return kXchgSlots + 2 * (size_t)world * (size_t)K * (D + 1) * sizeof(double);
+}
+
+extern "C" int gsl_kmeans_step_exchange(const float *data, int64_t N, int D, const float *centroids, int K,
+                                        int32_t *labels, int rank, int world, void *const *xbufs, uint64_t seq,
+                                        float *new_centroids, float *shift, double *sums,
+                                        void *ws, size_t ws_bytes, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = check_kd("gsl_kmeans_step_exchange", N, D, K)) return rc;
+    if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world) return fail(GSL_EINVAL, "gsl_kmeans_step_exchange: rank %d / world %d (at most %d ranks)", rank, world, kMaxRanks);
+    if (!centroids || !sums || !xbufs || !new_centroids || !shift || seq == 0) return fail(GSL_EINVAL, "gsl_kmeans_step_exchange: null pointer or seq == 0");
+    PeerTable peers;
+    for (int p = 0; p < kMaxRanks; ++p) {
+        peers.base[p] = p < world ? reinterpret_cast<unsigned char *>(xbufs[p]) : nullptr;
+        if (p < world && (!xbufs[p] || ((uintptr_t)xbufs[p] & 255))) return fail(GSL_EINVAL, "gsl_kmeans_step_exchange: exchange buffer %d is null or not 256-byte aligned", p);
+    }
+    const int n_el = K * (D + 1);
+    double *partials = nullptr;
+    int grid = 0;
+    if (N > 0) {
+        if (!data || !labels || !ws) return fail(GSL_EINVAL, "gsl_kmeans_step_exchange: null pointer");
+        if (ws_bytes < gsl_kmeans_workspace_bytes(N, D, K)) return fail(GSL_EWORKSPACE, "gsl_kmeans_step_exchange: workspace %zu < %zu", ws_bytes, gsl_kmeans_workspace_bytes(N, D, K));
+        partials = reinterpret_cast<double *>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+        grid = step_grid(N);
+        if (int rc = launch_step<true>(data, N, D, centroids, K, labels, partials, grid, st)) return rc;
+    }
+    kmeans_exchange_kernel<<<(n_el + 31) / 32, 256, 0, st>>>(partials, grid, n_el, peers, rank, world, (unsigned long long)seq,
+                                                              centroids, K, D, new_centroids, shift, sums);
+    GSL_LAUNCH_CHECK("kmeans_exchange_kernel");
     return GSL_OK;
 }
 

@@ -58,12 +58,13 @@ struct ColdView {
 
 // A window of views travels as a kernel parameter (constant bank 0), with the constants of the
 // screening bounds  ec = g_rm * (|X|+|Y|+|Z|) + g_tm  (camera coordinate) and
-// 1/2 - E = ec / cz * ek_neg + room0  (image coordinate) valid for all its views.
+// 1/2 - E = k * fxh_neg + room0 - (k + 3.04 u) |x|,  k = ec / cz  (image coordinate) valid for all
+// its views (lift.cu: screen_pair).
 template <int VW>
 struct ViewWindow {
     HotView h[VW];
     ColdView c[VW];
-    float g_rm, g_tm, ek_neg, room0;
+    float g_rm, g_tm, fxh_neg, room0;
 };
 
 // Byte offsets of the pieces of the lifting workspace (each 256-byte aligned).

@@ -18,8 +18,11 @@ Semantics kept from the reference (line numbers are the reference's):
             bit-identical centroids, hence identical trajectories;
   "fast"    float64 segmented sums, shardable; centroids agree with the reference to its own
             float32 rounding (about 1e-5 relative on clusters of 1e5 members).
-Under torch.distributed (world size > 1) each rank passes ITS rows; partial sums and counts
-are all-reduced with NCCL and `update` is forced to "fast".
+Under torch.distributed (world size > 1) each rank passes ITS rows and `update` is forced to
+"fast"; the partial sums and counts are exchanged inside the reduction kernel over peer memory
+(ops.KMeansExchange -> gsl_kmeans_step_exchange).  GSLIFT_KMEANS_EXCHANGE=nccl selects the
+three-step form instead (reduce kernel, NCCL all-reduce of K x (D+1) float64, finalize kernel),
+which is also what is used when torch cannot set up symmetric memory on the machine.
 """
 from __future__ import annotations
 
@@ -52,6 +55,28 @@ def _dist_world():
     return None
 
 
+_exchanges = {}
+
+
+def _make_exchange(centroids, dist):
+    """The fused exchange for this (K, D, device), or None when the three-step NCCL form is asked
+    for (GSLIFT_KMEANS_EXCHANGE=nccl) or symmetric memory cannot be set up.  Cached: the buffers are
+    a collective allocation."""
+    if os.environ.get("GSLIFT_KMEANS_EXCHANGE", "peer") == "nccl":
+        return None
+    key = (centroids.shape[0], centroids.shape[1], str(centroids.device), dist is not None)
+    if key not in _exchanges:
+        try:
+            _exchanges[key] = ops.KMeansExchange(centroids.shape[0], centroids.shape[1], centroids.device)
+        except Exception as exc:       # symmetric memory unavailable (no peer access, old torch): NCCL
+            import sys
+            if dist is None:
+                raise
+            print(f"gslift: peer-memory exchange unavailable ({exc}); using NCCL all-reduce", file=sys.stderr)
+            _exchanges[key] = None
+    return _exchanges[key]
+
+
 def lloyd(data, centroids, max_iter=100, tol=1e-4, update=None, verbose=True, device=None):
     """The iteration shared by both reference entry points, on device tensors.
 
@@ -66,11 +91,14 @@ def lloyd(data, centroids, max_iter=100, tol=1e-4, update=None, verbose=True, de
         raise ValueError(f"update must be 'ordered' or 'fast', not {update!r}")
     labels = torch.empty(data.shape[0], dtype=torch.int32, device=data.device)
     sums = torch.empty((centroids.shape[0], centroids.shape[1] + 1), dtype=torch.float64, device=data.device)
+    exchange = _make_exchange(centroids, dist) if update == "fast" else None
     done = 0
     for iteration in range(max_iter):
         if verbose:
             print(iteration)
-        if update == "fast":
+        if exchange is not None:
+            new_centroids, shift = exchange.step(data, centroids, labels)
+        elif update == "fast":
             ops.kmeans_step(data, centroids, labels, sums)
             if dist is not None:
                 dist.all_reduce(sums)                       # K x (D+1) float64 over NCCL

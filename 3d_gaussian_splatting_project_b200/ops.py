@@ -263,6 +263,60 @@ def kmeans_finalize(sums: torch.Tensor, old: torch.Tensor, new: torch.Tensor | N
     return new, shift
 
 
+class KMeansExchange:
+    """Per-job state of the fused K-means exchange (gsl_kmeans_step_exchange): this rank's exchange
+    buffer, everybody's peer-mapped pointers to it, and the call counter.
+
+    world == 1: an ordinary device buffer.  world > 1: a torch symmetric-memory allocation
+    (CUDA peer mapping over NVLink) rendezvoused over the process group, so that every rank's
+    kernel can store its partial sums straight into every other rank's buffer."""
+
+    def __init__(self, K: int, D: int, device: torch.device, group=None):
+        import ctypes
+        import torch.distributed as dist
+        self.K, self.D, self.device = int(K), int(D), torch.device(device)
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        nbytes = lib().gsl_kmeans_exchange_bytes(self.world, self.D, self.K)
+        if nbytes == 0:
+            raise ValueError(f"unsupported exchange shape: world={self.world}, K={K}, D={D}")
+        if self.world > 1:
+            import torch.distributed._symmetric_memory as symm_mem
+            grp = group if group is not None else dist.group.WORLD
+            self.buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self.buf.zero_()
+            self._handle = symm_mem.rendezvous(self.buf, grp.group_name)
+            ptrs = [int(p) for p in self._handle.buffer_ptrs]
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=grp)                # every buffer is zeroed before anyone pushes into it
+        else:
+            self.buf = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+            ptrs = [self.buf.data_ptr()]
+        self._ptrs = (ctypes.c_void_p * self.world)(*ptrs)
+        self.seq = 0
+        self.sums = torch.empty((self.K, self.D + 1), dtype=torch.float64, device=self.device)
+
+    def step(self, data: torch.Tensor, centroids: torch.Tensor, labels: torch.Tensor,
+             new: torch.Tensor | None = None, shift: torch.Tensor | None = None):
+        """One sharded Lloyd pass; returns (new centroids, shift); self.sums holds the totals.
+        A collective: every rank of the group must call it."""
+        N, D, K = _check_kmeans(data, centroids)
+        if (K, D) != (self.K, self.D):
+            raise ValueError("exchange was built for a different K, D")
+        if new is None:
+            new = torch.empty_like(centroids)
+        if shift is None:
+            shift = torch.empty(1, dtype=torch.float32, device=data.device)
+        L = lib()
+        ws = _ws.get(data.device, L.gsl_kmeans_workspace_bytes(N, D, K))
+        self.seq += 1
+        with torch.cuda.device(data.device):
+            check(L.gsl_kmeans_step_exchange(data.data_ptr(), N, D, centroids.data_ptr(), K, labels.data_ptr(),
+                                             self.rank, self.world, self._ptrs, self.seq, new.data_ptr(),
+                                             shift.data_ptr(), self.sums.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+        return new, shift
+
+
 def kmeans_update_ordered(data: torch.Tensor, labels: torch.Tensor, old: torch.Tensor):
     """Reference-order float32 sequential mean (km:125-128 bit for bit).  Single device."""
     N, D, K = _check_kmeans(data, old)

@@ -303,7 +303,15 @@ def run_native(a):
         sums = torch.empty((a.kmeans_k, a.kmeans_dim + 1), dtype=torch.float64, device=dev)
         new_c, shift = torch.empty_like(d_cen), torch.empty(1, dtype=torch.float32, device=dev)
 
+        # exchange of the K x (D+1) float64 sums: fused into the reduction kernel over peer memory
+        # (default), or reduce kernel + NCCL all-reduce + finalize kernel (GSLIFT_KMEANS_EXCHANGE=nccl)
+        use_peer = os.environ.get("GSLIFT_KMEANS_EXCHANGE", "peer") != "nccl"
+        xch = ops.KMeansExchange(a.kmeans_k, a.kmeans_dim, dev) if use_peer else None
+
         def k_iter(cen):
+            if xch is not None:
+                xch.step(d_feats, cen, k_labels, new_c, shift)
+                return
             ops.kmeans_step(d_feats, cen, k_labels, sums)
             if world > 1:
                 dist.all_reduce(sums)
@@ -327,11 +335,11 @@ def run_native(a):
         rows_r = khi - klo
         k_bytes = rows_r * (4 * a.kmeans_dim + 4) + 2 * a.kmeans_k * a.kmeans_dim * 4
         kres = {"metric": "kmeans_iters_per_s", "value": 1e3 / k_ms, "unit": "iters/s", "ms_per_iter": k_ms,
-                "update": "fast (float64 segmented sums" + (", NCCL all-reduce of K x (D+1) f64)" if world > 1 else ")"),
+                "update": "fast (float64 segmented sums" + ((", exchange of K x (D+1) f64 fused into the reduction kernel over peer memory)" if use_peer else ", NCCL all-reduce of K x (D+1) f64)") if world > 1 else ")"),
                 "roofline": {"bound": "hbm", "achieved": k_bytes / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": k_bytes / (k_ms * 1e-3) / 1e9 / peak, "traffic": ncu_traffic("kmeans_step_kernel"),
                              "algorithmic_bytes": k_bytes, "peak_source": peak_src},
-                "gpu_launches_per_iter": 3}
+                "gpu_launches_per_iter": 2 if use_peer else 3}
         if world == 1:
             # reference-order (bit-exact) update, single device
             oev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]

@@ -180,6 +180,29 @@ int gsl_kmeans_finalize(const double *sums, const float *old_centroids, int K, i
                         float *new_centroids, float *shift, void *stream);
 
 /*
+ * One Lloyd pass of a job sharded over `world` ranks (one process per GPU), with the exchange
+ * step fused into the reduction kernel: assignment + per-CTA sums as in gsl_kmeans_step, then ONE
+ * kernel that reduces the partials, pushes this rank's K x (D+1) float64 sums into every rank's
+ * exchange buffer over peer memory (NVLink), waits for the other ranks' sums, adds them in rank
+ * order (bit-identical totals on every rank) and forms the new centroids and the shift -- what
+ * gsl_kmeans_step + all-reduce + gsl_kmeans_finalize compute, without the collective library.
+ *   xbufs   HOST array of `world` device pointers; xbufs[r] = rank r's exchange buffer of
+ *           gsl_kmeans_exchange_bytes(world, D, K) bytes, 256-byte aligned, zeroed once before
+ *           first use, mapped into this process (peer access; e.g. torch symmetric memory).
+ *           world == 1: any device buffer of that size.
+ *   seq     exchange counter: 1 on the first call on these buffers, +1 per call, equal on all
+ *           ranks.  Every rank must make the call (it is a collective); a rank with N == 0 joins
+ *           with zero sums.
+ *   sums    float64 [K][D+1] out: the totals over all ranks.
+ *   shift   NaN if another rank did not arrive within 2 s.
+ */
+size_t gsl_kmeans_exchange_bytes(int world, int D, int K);
+int gsl_kmeans_step_exchange(const float *data, int64_t N, int D, const float *centroids, int K,
+                             int32_t *labels, int rank, int world, void *const *xbufs, uint64_t seq,
+                             float *new_centroids, float *shift, double *sums,
+                             void *ws, size_t ws_bytes, void *stream);
+
+/*
  * Reference-order update (km:125-128 exactly): every centroid coordinate is the float32
  * SEQUENTIAL sum of its members in index order, divided in float64 and rounded to float32
  * -- what NumPy's mean(axis=0) produces.  Single device only (the order cannot be sharded).

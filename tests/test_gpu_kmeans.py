@@ -231,3 +231,90 @@ def test_c5_shape_subsample_step_locked(oracle):
         assert np.array_equal(new_ord, ref_new)
         assert rel_exact < 1e-7 and rel_ref < 5e-5     # the reference's own float32 drift is ~1e-5 here
         cur = ref_new
+
+
+def test_fused_exchange_single_rank_equals_three_step_form():
+    """gsl_kmeans_step_exchange on one rank (the exchange pushes into its own buffer) must give
+    exactly what step + finalize give: same labels, same float64 totals, same centroids and shift,
+    over several calls (parity of the slots alternates) and for an empty shard."""
+    ops = pkg("ops")
+    rng = np.random.default_rng(21)
+    for n, d, k in ((40_000, 59, 64), (5_000, 6, 10), (777, 33, 17)):
+        data = rng.standard_normal((n, d)).astype(np.float32)
+        cen = dev(data[rng.choice(n, k, replace=False)])
+        d_data = dev(data)
+        xch = ops.KMeansExchange(k, d, d_data.device)
+        lab_x = torch.empty(n, dtype=torch.int32, device=DEV)
+        for it in range(3):
+            lab, sums = ops.kmeans_step(d_data, cen)
+            new, shift = ops.kmeans_finalize(sums, cen)
+            new_x, shift_x = xch.step(d_data, cen, lab_x)
+            assert torch.equal(lab_x, lab) and torch.equal(xch.sums, sums)
+            assert torch.equal(new_x, new) and torch.equal(shift_x, shift)
+            cen = new
+        empty = torch.empty((0, d), dtype=torch.float32, device=DEV)
+        new_e, shift_e = xch.step(empty, cen, torch.empty(0, dtype=torch.int32, device=DEV))
+        assert torch.equal(new_e, cen) and float(shift_e.item()) == 0.0 and float(xch.sums.abs().sum().item()) == 0.0
+
+
+_MGPU_WORKER = r'''
+import os, sys, importlib
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+gs = importlib.import_module("3d_gaussian_splatting_project_b200")
+ops, sharding, km = gs.ops, gs.sharding, gs.k_means
+rank, world, local = sharding.init_from_env("nccl")
+dev = torch.device("cuda", local)
+n, d, k = 400_003, 59, 64
+data = gs.scene.blob_features(n, d, n_blobs=64, seed=5)
+np.random.seed(0)
+cen0 = torch.from_numpy(data[np.random.choice(n, k, replace=False)]).to(dev)
+lo, hi = sharding.slice_bounds(n, rank, world)
+mine = torch.from_numpy(data[lo:hi]).to(dev)
+xch = ops.KMeansExchange(k, d, dev)
+lab = torch.empty(hi - lo, dtype=torch.int32, device=dev)
+cen = cen0.clone()
+for it in range(6):
+    # three-step form: reduce kernel, NCCL all-reduce, finalize kernel
+    lab_n, sums_n = ops.kmeans_step(mine, cen)
+    dist.all_reduce(sums_n)
+    new_n, shift_n = ops.kmeans_finalize(sums_n, cen)
+    # fused form over peer memory
+    new_x, shift_x = xch.step(mine, cen, lab)
+    assert torch.equal(lab, lab_n)
+    assert torch.equal(xch.sums[:, d], sums_n[:, d]), "member counts differ"
+    assert torch.allclose(xch.sums, sums_n, rtol=1e-13, atol=0), (xch.sums - sums_n).abs().max().item()
+    assert (new_x - new_n).abs().max().item() <= 1e-6 and abs(float(shift_x) - float(shift_n)) <= 1e-6
+    # every rank must hold bit-identical totals and centroids (rank-ordered sum)
+    gathered = [torch.empty_like(new_x) for _ in range(world)]
+    dist.all_gather(gathered, new_x)
+    assert all(torch.equal(g, gathered[0]) for g in gathered), "ranks disagree on the centroids"
+    cen = new_x
+# the drop-in loop on shards == the same loop on one device holding everything
+cen_s, lab_s, it_s = km.lloyd(mine, cen0, max_iter=4, tol=0.0, verbose=False)
+if rank == 0:
+    full = torch.from_numpy(data).to(dev)
+dist.barrier()
+whole = sharding.gather_labels(lab_s, n, rank, world)
+if rank == 0:
+    lab1, sums1 = ops.kmeans_step(full, cen_s)      # labels under the final centroids, one device
+    assert torch.equal(whole, lab1), int((whole != lab1).sum())
+torch.cuda.synchronize(); dist.barrier(); dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs on one node")
+def test_fused_exchange_over_peer_memory_two_ranks(tmp_path):
+    """One process per GPU: the fused exchange kernel against NCCL all-reduce, step by step."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "mgpu_worker.py"
+    script.write_text(_MGPU_WORKER)
+    n = min(torch.cuda.device_count(), 8)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+                          "--master-addr", "127.0.0.1", "--master-port", "29741", str(script), root],
+                         capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert out.stdout.count("ok") == n
