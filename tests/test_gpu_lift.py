@@ -236,3 +236,53 @@ def test_full_size_c3_properties_and_oracle(oracle):
     print(f"[C3 slice] {hi - lo} Gaussians x {v} views: visible pairs {vis} ({vis / ((hi - lo) * v):.1%}), "
           f"near-boundary Gaussians {int(near.sum())}, flips {flips}")
     assert flips == 0
+
+
+def test_float32_screening_hard_cases_against_oracle(oracle):
+    """Inputs chosen to sit on the float32 screening's decision edges: points on and next to the
+    camera plane (z ~ 0), projections a hair from pixel edges and from the image border, huge and
+    tiny coordinates (the bound turns NaN and everything is re-evaluated in float64), views far
+    from the origin (large |t|: loose bound, many re-evaluations), mixed frame sizes in one window.
+    The float32-screened sweep, the float64 sweep and the oracle must agree label for label."""
+    scene = pkg("scene")
+    rng = np.random.default_rng(77)
+    cams = scene.lookat_cameras(20, width=640, height=360, seed=31)
+    for i, c in enumerate(cams[:6]):                       # push six cameras far away: |t| grows, z stays positive
+        c["position"] = [float(v) * (50.0 + 400.0 * i) for v in c["position"]]
+    for c in cams[6:9]:                                    # other frame sizes inside the same 16-view window
+        c["width"], c["height"] = 320, 200
+    shapes = [(int(c["height"]), int(c["width"])) for c in cams]
+    maps = [scene.block_label_map(h, w, 1, -1, 149, 900 + i) for i, (h, w) in enumerate(shapes)]   # every pixel its own label
+    n = 60_000
+    pos = (rng.standard_normal((n, 3)) * 1.5).astype(np.float32)
+    views64 = oracle.make_views(cams, shapes)
+    # points constructed to project onto exact pixel edges of camera 10 (then nudged by a few float32 ulps)
+    R = np.array(cams[10]["rotation"]); p = np.array(cams[10]["position"])
+    k = 4000
+    px = rng.integers(0, 641, k).astype(np.float64); py = rng.integers(0, 361, k).astype(np.float64)
+    z = rng.uniform(3.0, 9.0, k)
+    cam_pts = np.stack([(px - 320.0) * z / cams[10]["fx"], (py - 180.0) * z / cams[10]["fy"], z], axis=1)
+    world = (np.linalg.inv(R) @ cam_pts.T).T + p
+    pos[:k] = world.astype(np.float32)
+    pos[k:2 * k] = np.nextafter(pos[:k], np.float32(np.inf))
+    pos[2 * k:3 * k] = np.nextafter(pos[:k], np.float32(-np.inf))
+    # points on the camera plane of camera 11 (z ~ 0 within rounding)
+    R = np.array(cams[11]["rotation"]); p = np.array(cams[11]["position"])
+    plane = np.stack([rng.uniform(-3, 3, 2000), rng.uniform(-3, 3, 2000), rng.uniform(-1e-6, 1e-6, 2000)], axis=1)
+    pos[3 * k:3 * k + 2000] = ((np.linalg.inv(R) @ plane.T).T + p).astype(np.float32)
+    pos[20000:20050] *= np.float32(1e20)                   # beyond the sanity limit of the float32 path
+    pos[20050:20100] *= np.float32(1e-30)
+    pos[20100] = [np.inf, 0.0, 0.0]; pos[20101] = [np.nan, 1.0, 1.0]; pos[20102] = [3e38, -3e38, 3e38]
+    flat = np.concatenate([m.reshape(-1) for m in maps])
+    with np.errstate(all="ignore"):
+        want, near, vis = oracle.lift_votes(pos, views64, flat, eps=1e-4, want_near=True)
+    got = gpu_lift(pos, cams, maps, None).cpu().numpy()
+    os.environ["GSLIFT_LIFT_F64"] = "1"
+    try:
+        got64 = gpu_lift(pos, cams, maps, None).cpu().numpy()
+    finally:
+        del os.environ["GSLIFT_LIFT_F64"]
+    assert np.array_equal(got, got64), f"float32-screened and float64 sweeps differ on {(got != got64).sum()} labels"
+    flips = compare(got, want, near)
+    print(f"[screening edges] visible pairs {vis}, near-boundary Gaussians {int(near.sum())}, flips {flips}")
+    assert flips == 0
