@@ -39,7 +39,7 @@ struct alignas(16) HotView {
     // width/2 - 1/2, height/2 - 1/2 (lift.cu: screen_pair)
     float R[9], t[3], half_w, half_h;
     float x_hi, y_hi;       // width + 2, height + 2: clamp range of the screened coordinate
-    const uint8_t *map;     // packed + map_offset
+    int64_t map_offset;     // byte offset of the view's packed map
     uint32_t pitch_m128;    // pitch - 128 and the folded constant of the float-derived offset
     uint32_t addr_k;        //   (lift.cu: screen_pair)
 };
@@ -67,9 +67,23 @@ struct ViewWindow {
     float g_rm, g_tm, fxh_neg, room0;
 };
 
+// One window of the float32 sweep as it lies in device memory (workspace): a single launch covers
+// many windows, block (tile, window) reads its window's entry.  gsl_lift_prepare uploads the table
+// of all 16-view windows once (entries [0, ceil(V / 16))), before any label map is in flight, so
+// the sweeps need no host-to-device copy of their own (it would queue behind the map uploads of a
+// pipelined caller); 8-view windows (view_window <= 8) are built per call behind that table.
+struct alignas(16) WinDev {
+    HotView h[16];
+    float g_rm, g_tm, fxh_neg, room0;
+    int n_live;        // views of the window (<= 16)
+    int border;        // every view has border_ok
+    int word0;         // first sheet word of the window = first_view / 4
+    int first_view;
+};
+
 // Byte offsets of the pieces of the lifting workspace (each 256-byte aligned).
 struct OrderWs {
-    size_t sheet, pos_sorted, perm, keys, keys_sorted, idx, sort_temp, sort_temp_bytes, stats, tilebox, masks, views, planes, bytes;
+    size_t sheet, pos_sorted, perm, keys, keys_sorted, idx, sort_temp, sort_temp_bytes, stats, tilebox, masks, views, planes, wins, bytes;
 };
 
 OrderWs order_layout(int64_t N, int V);

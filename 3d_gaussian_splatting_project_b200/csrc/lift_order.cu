@@ -296,6 +296,7 @@ OrderWs order_layout(int64_t N, int V)
     o.masks = take((size_t)n_tiles * (size_t)n_words16 * sizeof(uint16_t));
     o.views = take((size_t)(V > 0 ? V : 1) * sizeof(GslView));
     o.planes = take((size_t)(V > 0 ? V : 1) * 5 * sizeof(float4));
+    o.wins = take((size_t)((V + 15) / 16 + (V + 7) / 8 + 1) * sizeof(WinDev));
     o.bytes = off + 256;
     return o;
 }
