@@ -163,23 +163,34 @@ kmeans_step_kernel(const float *__restrict__ data, int64_t N, int D, const float
     }
 }
 
-// Fixed-order sum of the per-CTA partials.  A block owns 32 consecutive elements; its 8 warps
-// each add the partials p = w, w + 8, ... (coalesced 256-byte rows), then warp 0 adds the eight
-// warp sums in warp order -- the same grouping on every run, so the result is reproducible.
-__global__ void __launch_bounds__(256)
-kmeans_reduce_kernel(const double *__restrict__ partials, int n_parts, int n_el, double *__restrict__ sums)
+// Fixed-order sum of the per-CTA partials.  A block of 32 warps owns 32 consecutive elements; warp
+// w adds the partials p = w, w + 32, ... (coalesced 256-byte rows, a handful of independent loads
+// per thread), then warp 0 adds the 32 warp sums in warp order -- the same grouping on every run
+// and in both kernels that use it, so the result is reproducible.
+constexpr int kReduceThreads = 1024;
+
+__device__ __forceinline__ void reduce_partials(const double *__restrict__ partials, int n_parts, int n_el,
+                                                double (&part)[32][33], int i, int lane, int w)
 {
-    __shared__ double part[8][32];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int i = blockIdx.x * 32 + lane;
     double s = 0.0;
-    if (i < n_el)
-        for (int p = w; p < n_parts; p += 8) s += partials[(size_t)p * n_el + i];
+    if (i < n_el) {
+#pragma unroll 4
+        for (int p = w; p < n_parts; p += 32) s += __ldcs(partials + (size_t)p * n_el + i);
+    }
     part[w][lane] = s;
     __syncthreads();
+}
+
+__global__ void __launch_bounds__(kReduceThreads)
+kmeans_reduce_kernel(const double *__restrict__ partials, int n_parts, int n_el, double *__restrict__ sums)
+{
+    __shared__ double part[32][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + lane;
+    reduce_partials(partials, n_parts, n_el, part, i, lane, w);
     if (w == 0 && i < n_el) {
         double t = part[0][lane];
-        for (int ww = 1; ww < 8; ++ww) t += part[ww][lane];
+        for (int ww = 1; ww < 32; ++ww) t += part[ww][lane];
         sums[i] = t;
     }
 }
@@ -254,26 +265,22 @@ __device__ __forceinline__ unsigned long long global_ns()
     return t;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kReduceThreads)
 kmeans_exchange_kernel(const double *__restrict__ partials, int n_parts, int n_el, PeerTable peers, int rank, int world,
                        unsigned long long seq, const float *__restrict__ old_c, int K, int D,
                        float *__restrict__ new_c, float *__restrict__ shift, double *__restrict__ sums)
 {
-    __shared__ double part[8][32];
+    __shared__ double part[32][33];
     __shared__ int s_last, s_timeout;
-    __shared__ double red[8];
+    __shared__ double red[32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const size_t slot_off = kXchgSlots + ((size_t)(seq & 1ull) * world + rank) * (size_t)n_el * sizeof(double);
     {
         const int i = blockIdx.x * 32 + lane;
-        double s = 0.0;
-        if (i < n_el)
-            for (int p = w; p < n_parts; p += 8) s += partials[(size_t)p * n_el + i];
-        part[w][lane] = s;
-        __syncthreads();
+        reduce_partials(partials, n_parts, n_el, part, i, lane, w);
         if (w == 0 && i < n_el) {
             double t = part[0][lane];
-            for (int ww = 1; ww < 8; ++ww) t += part[ww][lane];
+            for (int ww = 1; ww < 32; ++ww) t += part[ww][lane];
             for (int p = 0; p < world; ++p)                                  // push: own sums into everyone's slot[rank]
                 reinterpret_cast<double *>(peers.base[p] + slot_off)[i] = t;
         }
@@ -319,7 +326,7 @@ kmeans_exchange_kernel(const double *__restrict__ partials, int n_parts, int n_e
     __syncthreads();
     if (threadIdx.x == 0) {
         double s = 0.0;
-        for (int ww = 0; ww < 8; ++ww) s += red[ww];
+        for (int ww = 0; ww < 32; ++ww) s += red[ww];
         *shift = s_timeout ? __int_as_float(0x7fc00000) : (float)sqrt(s);
     }
 }
@@ -442,7 +449,7 @@ extern "C" int gsl_kmeans_step(const float *data, int64_t N, int D, const float 
     double *partials = reinterpret_cast<double *>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
     const int grid = step_grid(N);
     if (int rc = launch_step<true>(data, N, D, centroids, K, labels, partials, grid, st)) return rc;
-    kmeans_reduce_kernel<<<(n_el + 31) / 32, 256, 0, st>>>(partials, grid, n_el, sums);
+    kmeans_reduce_kernel<<<(n_el + 31) / 32, kReduceThreads, 0, st>>>(partials, grid, n_el, sums);
     GSL_LAUNCH_CHECK("kmeans_reduce_kernel");
     return GSL_OK;
 }
@@ -477,7 +484,7 @@ extern "C" int gsl_kmeans_step_exchange(const float *data, int64_t N, int D, con
         grid = step_grid(N);
         if (int rc = launch_step<true>(data, N, D, centroids, K, labels, partials, grid, st)) return rc;
     }
-    kmeans_exchange_kernel<<<(n_el + 31) / 32, 256, 0, st>>>(partials, grid, n_el, peers, rank, world, (unsigned long long)seq,
+    kmeans_exchange_kernel<<<(n_el + 31) / 32, kReduceThreads, 0, st>>>(partials, grid, n_el, peers, rank, world, (unsigned long long)seq,
                                                               centroids, K, D, new_centroids, shift, sums);
     GSL_LAUNCH_CHECK("kmeans_exchange_kernel");
     return GSL_OK;

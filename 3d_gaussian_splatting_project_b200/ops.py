@@ -182,9 +182,10 @@ def lift_votes(pos: torch.Tensor, views: np.ndarray, packed: torch.Tensor,
 def lift_phases(pos: torch.Tensor, views: np.ndarray, packed: torch.Tensor,
                 label_min: int = DEFAULT_LABEL_MIN, n_classes: int = DEFAULT_N_CLASSES,
                 view_window: int = 0, out: torch.Tensor | None = None):
-    """lift_votes as its two ABI phases.  Returns (run_gather, run_majority, labels): two
-    zero-argument callables that enqueue gsl_lift_gather / gsl_lift_majority on the current
-    stream (benchmarks put events between them)."""
+    """lift_votes as its three ABI phases.  Returns (run_prepare, run_sweep, run_majority, labels):
+    zero-argument callables that enqueue gsl_lift_prepare (ordering + culling), gsl_lift_gather_range
+    over all views (the projection + gather sweep) and gsl_lift_majority on the current stream
+    (benchmarks put events between them)."""
     _require_cuda(pos, "pos")
     _require_cuda(packed, "packed")
     views = np.ascontiguousarray(views)
@@ -193,15 +194,18 @@ def lift_phases(pos: torch.Tensor, views: np.ndarray, packed: torch.Tensor,
     L = lib()
     ws = _ws.get(pos.device, L.gsl_lift_workspace_bytes(N, V))
 
-    def run_gather():
-        check(L.gsl_lift_gather(pos.data_ptr(), N, views.ctypes.data, V, packed.data_ptr(), None, 0.0,
-                                int(view_window), ws.data_ptr(), ws.numel(), _stream()))
+    def run_prepare():
+        check(L.gsl_lift_prepare(pos.data_ptr(), N, views.ctypes.data, V, ws.data_ptr(), ws.numel(), _stream()))
+
+    def run_sweep():
+        check(L.gsl_lift_gather_range(pos.data_ptr(), N, views.ctypes.data, V, 0, V, packed.data_ptr(), None, 0.0,
+                                      int(view_window), ws.data_ptr(), ws.numel(), _stream()))
 
     def run_majority():
         check(L.gsl_lift_majority(N, V, int(label_min), int(n_classes), labels.data_ptr(),
                                   ws.data_ptr(), ws.numel(), _stream()))
 
-    return run_gather, run_majority, labels
+    return run_prepare, run_sweep, run_majority, labels
 
 
 # --------------------------------------------------------------------------------------

@@ -10,10 +10,10 @@ one GPU): 6M Gaussians x 300 views of 1920x1080 label maps with 151 label values
 K=64 on 6M x 59 float32 features.  Total work is fixed; Gaussians (rows) are split across the
 ranks, every view is replicated ("scaling": "strong").  Data is synthetic (scene.py).
 
-One "step" = one lifting pass over this rank's Gaussians and all views (gsl_lift_gather +
-gsl_lift_majority) with positions and packed maps resident in HBM.  K-means iterations
-(gsl_kmeans_step + all-reduce + gsl_kmeans_finalize) are timed the same way and reported
-under "kmeans".  `e2e` is the same lifting through the public Python entry point
+One "step" = one lifting pass over this rank's Gaussians and all views (gsl_lift_prepare +
+gsl_lift_gather_range + gsl_lift_majority) with positions and packed maps resident in HBM.
+K-means iterations (gsl_kmeans_step_exchange: assignment + sums, then reduction fused with the
+cross-rank exchange and the update) are timed the same way and reported under "kmeans".  `e2e` is the same lifting through the public Python entry point
 (deep_learning_segmentation.lift_labels) with pinned HOST inputs: int32 maps and positions
 are copied to the device and labels copied back inside the timed region.
 
@@ -261,7 +261,7 @@ def run_native(a):
     torch.cuda.synchronize()
     pack_ms = pack_ev[0].elapsed_time(pack_ev[1]) / 5 * (V / n_chunk)
     del chunk, scratch
-    run_gather, run_majority, labels = ops.lift_phases(d_pos, views, packed, -1, 151, view_window=a.view_window)
+    run_prepare, run_sweep, run_majority, labels = ops.lift_phases(d_pos, views, packed, -1, 151, view_window=a.view_window)
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -269,24 +269,27 @@ def run_native(a):
 
     # ---- lifting, device resident
     for _ in range(a.warmup):
-        run_gather(); run_majority()
+        run_prepare(); run_sweep(); run_majority()
     barrier()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * a.steps)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4 * a.steps)]
     t_wall0 = time.time()
     for i in range(a.steps):
-        ev[3 * i].record(); run_gather()
-        ev[3 * i + 1].record(); run_majority()
-        ev[3 * i + 2].record()
+        ev[4 * i].record(); run_prepare()
+        ev[4 * i + 1].record(); run_sweep()
+        ev[4 * i + 2].record(); run_majority()
+        ev[4 * i + 3].record()
     barrier()
     t_wall1 = time.time()
     total_ms = ev[0].elapsed_time(ev[-1])
-    gather_ms = float(np.mean([ev[3 * i].elapsed_time(ev[3 * i + 1]) for i in range(a.steps)]))
-    major_ms = float(np.mean([ev[3 * i + 1].elapsed_time(ev[3 * i + 2]) for i in range(a.steps)]))
+    order_ms = float(np.mean([ev[4 * i].elapsed_time(ev[4 * i + 1]) for i in range(a.steps)]))
+    gather_ms = float(np.mean([ev[4 * i + 1].elapsed_time(ev[4 * i + 2]) for i in range(a.steps)]))
+    major_ms = float(np.mean([ev[4 * i + 2].elapsed_time(ev[4 * i + 3]) for i in range(a.steps)]))
     total_ms = sharding.barrier_max_ms(total_ms, dev)
     ms_per_step = total_ms / a.steps
     value = a.gaussians * V / (ms_per_step * 1e-3)
-    # kernels of one lifting step: 12 ordering/culling kernels (5 of them the radix sort), one gather per 16-view window, 1 majority
-    n_lift_launches = 12 + (V + 15) // 16 + 1
+    # kernels of one lifting step: 11 ordering/culling kernels (5 of them the radix sort), ONE sweep
+    # launch over (tile, window) for all float32-screened windows, 1 majority
+    n_lift_launches = 11 + 1 + 1
     label_hist = torch.bincount((labels + 1).clamp(min=0).long(), minlength=152)[:3].tolist()
 
     # ---- K-means, device resident
@@ -413,11 +416,12 @@ def run_native(a):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(a),
-            "kernels_ms": {"lift_gather_kernel": gather_ms, "lift_majority_kernel": major_ms, "pack_labels_all_views_staging": pack_ms},
+            "kernels_ms": {"order_and_cull (11 kernels)": order_ms, "lift_gather_f32_kernel": gather_ms, "lift_majority_kernel": major_ms,
+                           "pack_labels_all_views_staging": pack_ms},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": ncu_traffic("lift_gather_kernel"), "kernel": "lift_gather_kernel",
+                         "traffic": ncu_traffic("lift_gather_f32_kernel"), "kernel": "lift_gather_f32_kernel",
                          "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
-                         "note": "algorithmic bytes = 16 N_r + 1 V H W (SURVEY 8d, uint8 maps); the kernel is FP64-issue / L1-gather limited, see DESIGN.md"},
+                         "note": "algorithmic bytes = 16 N_r + 1 V H W (SURVEY 8d, uint8 maps), one launch sweeps all views; the kernel is instruction-issue bound (~50 instructions per pair, float32 screening + float64 re-evaluation), see DESIGN.md"},
             "cpu_baseline": cpu, "e2e": e2e, "kmeans": kres,
             "gpu_launches": a.steps * n_lift_launches,
             "clocks": clocks, "clocks_window": "lifting + k-means timed regions, nvidia-smi -lms 20", "label_histogram_head": label_hist,
