@@ -101,3 +101,43 @@ def test_kmeans_path_boundaries(oracle, n, d, k):
         m = want == c
         assert s[c, d] == m.sum()
         assert np.allclose(s[c, :d], data[m].astype(np.float64).sum(0), rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_screened_sweep_equals_float64_sweep_on_random_configs(oracle, seed, monkeypatch):
+    """Differential test of the two sweeps (float32-screened default, GSLIFT_LIFT_F64=1) and the
+    oracle over random scenes that mix, inside one 16-view window, integer frames with and
+    without rescaling, maps larger and smaller than the frame (clamp active), one non-integer
+    frame (sent to the float64 kernel), and intrinsics from wide-angle to telephoto."""
+    ops, scene = pkg("ops"), pkg("scene")
+    rng = np.random.default_rng(500 + seed)
+    V = int(rng.integers(17, 40))
+    cams = scene.lookat_cameras(V, width=200, height=120, seed=600 + seed)
+    shapes, sizes = [], []
+    for i, c in enumerate(cams):
+        w, h = int(rng.integers(40, 400)), int(rng.integers(30, 300))
+        c["width"], c["height"] = w, h
+        c["fx"], c["fy"] = float(rng.uniform(0.3, 6.0) * w), float(rng.uniform(0.3, 6.0) * h)
+        mode = int(rng.integers(0, 4))
+        if mode == 0:                                   # map == frame, unit scale: zero-ring variant
+            shapes.append((h, w)); sizes.append((w, h))
+        elif mode == 1:                                 # map != frame, unit scale (clamp may fire)
+            shapes.append((int(rng.integers(10, 300)), int(rng.integers(10, 400)))); sizes.append((shapes[-1][1], shapes[-1][0]))
+        else:                                           # rescaled
+            shapes.append((int(rng.integers(10, 300)), int(rng.integers(10, 400)))); sizes.append((int(rng.integers(20, 500)), int(rng.integers(20, 500))))
+    if seed % 2:
+        cams[3]["width"] = cams[3]["width"] + 0.5       # non-integer frame: its window takes the float64 kernel
+    maps = [rng.integers(-1, 150, size=s).astype(np.int32) for s in shapes]
+    pos = (rng.standard_normal((30_000, 3)) * rng.uniform(0.5, 3.0)).astype(np.float32)
+    flat = np.concatenate([m.reshape(-1) for m in maps])
+    want, _, _ = oracle.lift_votes(pos, oracle.make_views(cams, shapes, sizes), flat)
+    views = ops.make_views(cams, shapes, sizes)
+    packed = ops.pack_labels(torch.from_numpy(flat).to(DEV), shapes)
+    d_pos = torch.from_numpy(pos).to(DEV)
+    got = ops.lift_votes(d_pos, views, packed).cpu().numpy()
+    monkeypatch.setenv("GSLIFT_LIFT_F64", "1")
+    got64 = ops.lift_votes(d_pos, views, packed).cpu().numpy()
+    monkeypatch.delenv("GSLIFT_LIFT_F64")
+    got8 = ops.lift_votes(d_pos, views, packed, view_window=8).cpu().numpy()
+    assert np.array_equal(got, got64) and np.array_equal(got, got8)
+    assert np.array_equal(got, want), f"{(got != want).sum()} labels differ from the oracle"
