@@ -10,8 +10,10 @@
 //      a 32-row x 64-centroid block are TF32 mma.sync.m16n8k8 (operands rounded with
 //      cvt.rna.tf32, FP32 accumulate).  |g_k - exact| <= E_k = 1.5 * 2^-9 |x'| |c'_k| +
 //      2^-22 (|x'| + |c'_k|)^2 (operand rounding 2^-11 each, doubled by the factor 2, 1.5x margin
-//      for the accumulation; second term: rounding of the centring itself).  Candidates =
-//      { k : g_k - E_k <= min_j (g_j + E_j) }.  Typically one or two per row.
+//      for the accumulation; second term: rounding of the centring itself).  The kernel uses the
+//      row-wide bound E = max_k E_k (one value per row instead of one per pair):  candidates =
+//      { k : g_k <= min_j g_j + 2 E }, a superset of { k : g_k - E_k <= min_j (g_j + E_j) }.
+//      Typically one or two per row.
 //   B  CUDA cores, candidates only: float32 sum of (x-c)^2 on the original values, relative
 //      error (D + 3) 2^-24; decided when the two smallest differ by more than that.
 //   C  float64, near ties only: scipy-order distance, lowest index first.
@@ -323,6 +325,9 @@ kmeans_step_tc_kernel(const float *__restrict__ data, int64_t N, int D, const fl
         eab[2 * t + 1] = 4.76837158203125e-7f * ncu * ncu * 1.0001f;   // 2^-21 |c'_k|^2
     }
     __syncthreads();
+    // row-wide bound: the largest ea_k, eb_k over the real centroids (both grow with |c'_k|)
+    float ea_max = 0.f, eb_max = 0.f;
+    for (int k = 0; k < K; ++k) { ea_max = fmaxf(ea_max, eab[2 * k]); eb_max = fmaxf(eb_max, eab[2 * k + 1]); }
     for (int i = t; i < kTcKP * kTcCPitch; i += kTcThreads) cprime[i] = __uint_as_float(to_tf32(cprime[i]));
     if (kAccumulate)
         for (int i = t; i < K * (D + 1); i += kTcThreads) acc[i] = 0.0;
@@ -363,28 +368,22 @@ kmeans_step_tc_kernel(const float *__restrict__ data, int64_t N, int D, const fl
             for (int h = 0; h < 2; ++h) {
                 const float nx = so.nx[mt][h];
                 const float nx_term = 4.76837158203125e-7f * nx * nx * 1.0001f;        // 2^-21 |x'|^2
-                float up = INFINITY;
-                float lo[16];
+                // smallest ranking value of the row, then every k within 2 E of it (padded centroids
+                // carry g = +inf and never qualify)
+                float gmin = INFINITY;
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        const int n = 8 * j + 2 * tq + c;
-                        const float gk = so.g[mt][j][2 * h + c];
-                        const float2 ab = *reinterpret_cast<const float2 *>(eab + 2 * n);
-                        const float e = screen_bound(nx, nx_term, ab.x, ab.y);
-                        up = fminf(up, gk + e);
-                        lo[2 * j + c] = gk - e;
-                    }
-                up = fminf(up, __shfl_xor_sync(0xffffffffu, up, 1));
-                up = fminf(up, __shfl_xor_sync(0xffffffffu, up, 2));
+                    gmin = fminf(gmin, fminf(so.g[mt][j][2 * h], so.g[mt][j][2 * h + 1]));
+                gmin = fminf(gmin, __shfl_xor_sync(0xffffffffu, gmin, 1));
+                gmin = fminf(gmin, __shfl_xor_sync(0xffffffffu, gmin, 2));
+                const float thr = gmin + 2.f * (screen_bound(nx, nx_term, ea_max, eb_max) * 1.000001f);
                 unsigned m_lo = 0, m_hi = 0;
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
                         const int n = 8 * j + 2 * tq + c;
-                        const unsigned bit = (lo[2 * j + c] <= up) ? 1u : 0u;
+                        const unsigned bit = (so.g[mt][j][2 * h + c] <= thr) ? 1u : 0u;
                         if (n < 32) m_lo |= bit << n; else m_hi |= bit << (n - 32);
                     }
                 m_lo |= __shfl_xor_sync(0xffffffffu, m_lo, 1); m_hi |= __shfl_xor_sync(0xffffffffu, m_hi, 1);
