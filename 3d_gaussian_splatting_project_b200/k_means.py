@@ -107,6 +107,9 @@ def lloyd(data, centroids, max_iter=100, tol=1e-4, update=None, verbose=True, de
             ops.kmeans_assign(data, centroids, labels)
             new_centroids, shift = ops.kmeans_update_ordered(data, labels, centroids)
         shift_value = np.float32(shift.item())
+        if exchange is not None and exchange.world > 1 and np.isnan(shift_value):
+            raise RuntimeError("K-means exchange returned a NaN shift: a rank did not reach the exchange within "
+                               "2 s (every rank must call lloyd with the same max_iter/tol), or the data is not finite")
         done = iteration + 1
         if verbose:
             print(shift_value)

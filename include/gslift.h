@@ -114,8 +114,9 @@ size_t gsl_lift_workspace_bytes(int64_t N, int V);
  *   near       optional uint8 [N] out (may be NULL): 1 when some (Gaussian, view) has an
  *              image coordinate within near_eps px of an integer or |z_cam| < near_eps --
  *              the set exempt from bit-exactness in the parity criterion.
- *   view_window  views swept per launch over all Gaussians: <= 8 selects 8, anything else
- *              (0 = default) 16; results do not depend on it.
+ *   view_window  views per window -- the set of label maps all SMs sweep together, i.e. what L2
+ *              holds at a time: <= 8 selects 8, anything else (0 = default) 16; results do not
+ *              depend on it.  All windows the float32 screening covers are swept by one launch.
  */
 int gsl_lift_votes(const float *pos, int64_t N, const GslView *views, int V,
                    const uint8_t *packed, int label_min, int n_classes, int32_t *labels,
@@ -132,7 +133,7 @@ int gsl_lift_gather(const float *pos, int64_t N, const GslView *views, int V,
                     void *ws, size_t ws_bytes, void *stream);
 /*
  * gsl_lift_gather in two steps, so that views can be swept while later maps are still being
- * uploaded: prepare orders the Gaussians and decides which (tile, view) pairs can be skipped (it
+ * uploaded: prepare uploads the view tables, orders the Gaussians and decides which (tile, view) pairs can be skipped (it
  * reads camera parameters only, no maps); gather_range sweeps views [v_begin, v_end), v_begin a
  * multiple of 16, whose packed maps must be resident.  gsl_lift_gather == prepare + range(0, V).
  * `near` (if used) must be zeroed by the caller before the first range.
