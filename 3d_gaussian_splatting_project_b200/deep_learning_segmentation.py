@@ -166,50 +166,74 @@ def _stage_maps(seg_maps, shapes, device, label_min, n_classes):
 _copy_streams = {}
 
 
-def _lift_pipelined(pos, views, seg_maps, shapes, device):
+def _lift_pipelined(positions, cameras, image_sizes, seg_maps, shapes, device):
     """One-process fast path of lift_labels: the maps are uploaded 16 views at a time on a copy
     stream while the compute stream packs and sweeps the previous 16 (gsl_lift_prepare +
     gsl_lift_gather_range), so everything but the last window hides behind the PCIe transfer and
-    only two 16-view staging buffers exist on the device.  Codes are label + 2 (label_min = -1);
+    only two 16-view staging buffers exist on the device.  The first uploads are enqueued before
+    anything else happens on the host (the view table of 300 cameras takes milliseconds of NumPy),
+    because the PCIe transfer is what the call waits for.  Codes are label + 2 (label_min = -1);
     returns None when the labels do not fit that window and the caller must take the general path."""
     from ._native import check, lib
     L = lib()
-    N, V = pos.shape[0], len(views)
+    V = len(seg_maps)
     sizes = [h * w for h, w in shapes]
     starts = np.concatenate(([0], np.cumsum(sizes))).astype(np.int64)     # pixels, row-major staging
     pstarts = ops.packed_offsets(shapes)                                   # bytes, packed layout
-    packed = torch.empty(int(pstarts[-1]), dtype=torch.uint8, device=device)
-    ws = ops._ws.get(device, L.gsl_lift_workspace_bytes(N, V))
     main = torch.cuda.current_stream(device)
     key = (device.type, device.index)
     if key not in _copy_streams:
         _copy_streams[key] = torch.cuda.Stream(device)
     copy = _copy_streams[key]
     CH = 16
-    chunk_px = max(int(starts[min(v0 + CH, V)] - starts[v0]) for v0 in range(0, V, CH))
+    chunks = list(range(0, V, CH))
+    chunk_px = max(int(starts[min(v0 + CH, V)] - starts[v0]) for v0 in chunks)
     slots = [torch.empty(chunk_px, dtype=torch.int32, device=device) for _ in range(2)]
     slot_free = [None, None]
-    minmax = torch.tensor([2**31 - 1, -2**31], dtype=torch.int32, device=device)
-    err = torch.zeros(1, dtype=torch.int32, device=device)
-    vptr = views.ctypes.data
+    ready = [None] * len(chunks)
+
+    def upload(ci):
+        v0 = chunks[ci]
+        v1 = min(v0 + CH, V)
+        buf = slots[ci % 2]
+        with torch.cuda.stream(copy):
+            if slot_free[ci % 2] is not None:
+                copy.wait_event(slot_free[ci % 2])
+            off = 0
+            for v in range(v0, v1):
+                m = seg_maps[v]
+                src = m if isinstance(m, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(m, np.int32))
+                buf[off:off + sizes[v]].copy_(src.reshape(-1), non_blocking=True)
+                off += sizes[v]
+            ready[ci] = torch.cuda.Event()
+            ready[ci].record(copy)
+        return off
+
+    trace = os.environ.get("GSLIFT_TRACE") == "1"               # phase timings of this call on stderr
     with torch.cuda.device(device):
+        if trace:
+            import sys, time
+            t_host0 = time.perf_counter()
+            print(f"[gslift trace] pipeline starts at {t_host0:.6f}", file=sys.stderr)
+            ev0 = torch.cuda.Event(enable_timing=True); ev0.record(main)
+        n_px = [0] * len(chunks)
+        for ci in range(min(2, len(chunks))):                   # the transfer starts now
+            n_px[ci] = upload(ci)
+        pos = positions if isinstance(positions, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(positions, np.float32))
+        pos = pos.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+        views = ops.make_views(cameras, shapes, image_sizes)
+        N = pos.shape[0]
+        packed = torch.empty(int(pstarts[-1]), dtype=torch.uint8, device=device)
+        ws = ops._ws.get(device, L.gsl_lift_workspace_bytes(N, V))
+        minmax = torch.tensor([2**31 - 1, -2**31], dtype=torch.int32, device=device)
+        err = torch.zeros(1, dtype=torch.int32, device=device)
+        vptr = views.ctypes.data
         check(L.gsl_lift_prepare(pos.data_ptr(), N, vptr, V, ws.data_ptr(), ws.numel(), main.cuda_stream))
-        for ci, v0 in enumerate(range(0, V, CH)):
+        for ci, v0 in enumerate(chunks):
             v1 = min(v0 + CH, V)
             buf = slots[ci % 2]
-            with torch.cuda.stream(copy):
-                if slot_free[ci % 2] is not None:
-                    copy.wait_event(slot_free[ci % 2])
-                off = 0
-                for v in range(v0, v1):
-                    m = seg_maps[v]
-                    src = m if isinstance(m, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(m, np.int32))
-                    buf[off:off + sizes[v]].copy_(src.reshape(-1), non_blocking=True)
-                    off += sizes[v]
-                ready = torch.cuda.Event()
-                ready.record(copy)
-            main.wait_event(ready)
-            check(L.gsl_label_range(buf.data_ptr(), off, minmax.data_ptr(), main.cuda_stream))
+            main.wait_event(ready[ci])
+            check(L.gsl_label_range(buf.data_ptr(), n_px[ci], minmax.data_ptr(), main.cuda_stream))
             v = v0
             while v < v1:                                # one pack launch per run of equal shapes
                 n = 1
@@ -220,13 +244,25 @@ def _lift_pipelined(pos, views, seg_maps, shapes, device):
                 v += n
             slot_free[ci % 2] = torch.cuda.Event()
             slot_free[ci % 2].record(main)
+            if ci + 2 < len(chunks):
+                n_px[ci + 2] = upload(ci + 2)            # refills the slot just packed
             check(L.gsl_lift_gather_range(pos.data_ptr(), N, vptr, V, v0, v1, packed.data_ptr(), None, 0.0, 0,
                                           ws.data_ptr(), ws.numel(), main.cuda_stream))
+        if trace:
+            t_host1 = time.perf_counter()
+            ev_up = torch.cuda.Event(enable_timing=True); ev_up.record(copy)
+            ev_sw = torch.cuda.Event(enable_timing=True); ev_sw.record(main)
         lo, hi = (int(x) for x in minmax.tolist())           # synchronises: every copy has been consumed
         if lo < -1 or hi > 253:
             return None
         labels = torch.empty(N, dtype=torch.int32, device=device)
         check(L.gsl_lift_majority(N, V, -1, max(hi + 2, 1), labels.data_ptr(), ws.data_ptr(), ws.numel(), main.cuda_stream))
+        if trace:
+            import sys
+            ev_mj = torch.cuda.Event(enable_timing=True); ev_mj.record(main)
+            ev_mj.synchronize()
+            print(f"[gslift trace] majority done at {time.perf_counter():.6f} | host enqueue {1e3 * (t_host1 - t_host0):.2f} ms | uploads done +{ev0.elapsed_time(ev_up):.2f} ms | "
+                  f"last sweep done +{ev0.elapsed_time(ev_sw):.2f} ms | majority done +{ev0.elapsed_time(ev_mj):.2f} ms", file=sys.stderr)
     return labels
 
 
@@ -241,17 +277,21 @@ def lift_labels(positions, cameras, seg_maps, image_sizes=None, device=None, wan
     Returns int32 NumPy labels (and the near-boundary mask when want_near).
     """
     device = torch.device(device if device is not None else "cuda")
-    pos = positions if isinstance(positions, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(positions, np.float32))
-    pos = pos.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+    if os.environ.get("GSLIFT_TRACE") == "1":
+        import sys, time
+        print(f"[gslift trace] lift_labels entered at {time.perf_counter():.6f}", file=sys.stderr)
     shapes = [tuple(m.shape) for m in seg_maps]
-    views = ops.make_views(cameras, shapes, image_sizes)
+    n_pos = positions.shape[0]
     import torch.distributed as dist
     single = not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
-    if (single and not want_near and label_min is None and n_classes is None and len(views) and pos.shape[0]
+    if (single and not want_near and label_min is None and n_classes is None and len(cameras) and n_pos
             and all(len(sh) == 2 for sh in shapes)):
-        fast = _lift_pipelined(pos, views, seg_maps, shapes, device)
+        fast = _lift_pipelined(positions, cameras, image_sizes, seg_maps, shapes, device)
         if fast is not None:
             return _to_host(fast)
+    pos = positions if isinstance(positions, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(positions, np.float32))
+    pos = pos.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+    views = ops.make_views(cameras, shapes, image_sizes)
     packed, label_min, n_classes = _stage_maps(seg_maps, shapes, device, label_min, n_classes)
     res = ops.lift_votes(pos, views, packed, label_min, n_classes, want_near=want_near, near_eps=near_eps)
     if want_near:
@@ -262,9 +302,17 @@ def lift_labels(positions, cameras, seg_maps, image_sizes=None, device=None, wan
 def _to_host(t: torch.Tensor) -> np.ndarray:
     """Device tensor -> NumPy through a pinned staging tensor (a pageable `.cpu()` of 24 MB costs
     ~10 ms; pinned, it is PCIe speed).  The array owns its pinned storage."""
+    trace = os.environ.get("GSLIFT_TRACE") == "1"
+    if trace:
+        import sys, time
+        t0 = time.perf_counter()
     host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    if trace:
+        t1 = time.perf_counter()
     host.copy_(t, non_blocking=True)
     torch.cuda.current_stream(t.device).synchronize()
+    if trace:
+        print(f"[gslift trace] result to host: pinned alloc {1e3 * (t1 - t0):.2f} ms, copy {1e3 * (time.perf_counter() - t1):.2f} ms", file=sys.stderr)
     return host.numpy()
 
 
