@@ -56,15 +56,11 @@ struct ColdView {
                        // land in the zero ring of the tiled map, no bounds test needed
 };
 
-// A window of views travels as a kernel parameter (constant bank 0), with the constants of the
-// screening bounds  ec = g_rm * (|X|+|Y|+|Z|) + g_tm  (camera coordinate) and
-// 1/2 - E = k * fxh_neg + room0 - (k + 3.04 u) |x|,  k = ec / cz  (image coordinate) valid for all
-// its views (lift.cu: screen_pair).
+// A window of views as the float64 kernel (lift_gather_kernel) takes it: by value, as a kernel
+// parameter (constant bank 0, compile-time offsets).
 template <int VW>
 struct ViewWindow {
-    HotView h[VW];
     ColdView c[VW];
-    float g_rm, g_tm, fxh_neg, room0;
 };
 
 // One window of the float32 sweep as it lies in device memory (workspace): a single launch covers
@@ -74,6 +70,9 @@ struct ViewWindow {
 // pipelined caller); 8-view windows (view_window <= 8) are built per call behind that table.
 struct alignas(16) WinDev {
     HotView h[16];
+    // constants of the screening bounds, valid for all views of the window (lift.cu: screen_pair):
+    // ec = g_rm * (|X|+|Y|+|Z|) + g_tm  (camera coordinate) and
+    // 1/2 - E = k * fxh_neg + room0 - (k + 3.04 u) |x|,  k = ec / cz  (image coordinate)
     float g_rm, g_tm, fxh_neg, room0;
     int n_live;        // views of the window (<= 16)
     int border;        // every view has border_ok
@@ -87,8 +86,7 @@ struct OrderWs {
 };
 
 OrderWs order_layout(int64_t N, int V);
-int order_gaussians(const float *pos, int64_t N, const GslView *views, int V, unsigned char *base,
-                    const OrderWs &L, cudaStream_t st);
+int order_gaussians(const float *pos, int64_t N, int V, unsigned char *base, const OrderWs &L, cudaStream_t st);
 
 // lift_sort.cu: stable radix sort of (24-bit cell key, row index) pairs.
 size_t sort_temp_capacity(int64_t N);

@@ -302,9 +302,8 @@ OrderWs order_layout(int64_t N, int V)
 }
 
 // Sort positions into Morton order, box the tiles, and decide per (tile, view) whether the view
-// must be swept.  All launches on `st`; `views` is the caller's host table.
-int order_gaussians(const float *pos, int64_t N, const GslView *views, int V, unsigned char *base,
-                    const OrderWs &L, cudaStream_t st)
+// must be swept.  All launches on `st`; the view table is already in the workspace (gsl_lift_prepare).
+int order_gaussians(const float *pos, int64_t N, int V, unsigned char *base, const OrderWs &L, cudaStream_t st)
 {
     float *pos_sorted = reinterpret_cast<float *>(base + L.pos_sorted);
     int32_t *perm = reinterpret_cast<int32_t *>(base + L.perm);
@@ -319,7 +318,6 @@ int order_gaussians(const float *pos, int64_t N, const GslView *views, int V, un
     const int64_t n_tiles = (N + kSheetTile - 1) / kSheetTile;
     const int n_words16 = (V + 15) / 16;
 
-    (void)views;                                   // already in the workspace (gsl_lift_prepare)
     GSL_CUDA_TRY(cudaMemsetAsync(stats, 0xff, 3 * 8, st));
     GSL_CUDA_TRY(cudaMemsetAsync(stats + 3, 0x00, kStatsBytes - 3 * 8, st));
     int64_t blocks = (N + 256 * 8 - 1) / (256 * 8);
