@@ -79,3 +79,38 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "import oracle" not in text and "from oracle" not in text, f
                 assert "libgsl_oracle" not in text, f
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/gslift.h must compile as C (no C++, no torch types) and a C program must be able to
+    call the library: the boundary a non-Python host would bind."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    native = pkg("_native")
+    src = tmp_path / "abi_probe.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "gslift.h"
+int main(void)
+{
+    GslView v;
+    if (sizeof(v) != 176) return 2;
+    if (gsl_version() != GSL_ABI_VERSION) return 3;
+    if (gsl_packed_map_bytes(1920, 1080) != 122LL * 137 * 128) return 4;
+    if (gsl_kmeans_exchange_bytes(8, 59, 64) != 256 + 2u * 8 * 64 * 60 * 8) return 5;
+    if (gsl_lift_votes(NULL, -1, NULL, 0, NULL, -1, 255, NULL, NULL, 0.0, 0, NULL, 0, NULL) != GSL_EINVAL) return 6;
+    if (strlen(gsl_last_error()) == 0) return 7;
+    printf("abi ok %d\n", gsl_version());
+    return 0;
+}
+''')
+    exe = tmp_path / "abi_probe"
+    lib_dir = os.path.dirname(native.LIB_PATH)
+    cc = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                         "-L", lib_dir, "-lgslift", f"-Wl,-rpath,{lib_dir}"], capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert run.returncode == 0 and "abi ok 2" in run.stdout, (run.returncode, run.stdout, run.stderr)
