@@ -39,6 +39,8 @@ SIGNATURES = {
     "gsl_device_count": (_i32, []),
     "gsl_packed_map_bytes": (_i64, [_i32, _i32]),
     "gsl_pack_labels": (_i32, [_vp, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _vp]),
+    "gsl_host_pack_labels": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _vp, _vp]),
+    "gsl_tile_codes": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "gsl_label_range": (_i32, [_vp, _i64, _vp, _vp]),
     "gsl_lift_workspace_bytes": (_sz, [_i64, _i32]),
     "gsl_lift_votes": (_i32, [_vp, _i64, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _dbl, _i32, _vp, _sz, _vp]),

@@ -1,0 +1,137 @@
+// Hybrid label-map staging.  lift_labels from HOST int32 maps is bound by
+// the PCIe transfer of 4 bytes per pixel.  The host cores can narrow maps to the 1-byte codes
+// while the DMA engine moves other maps as int32, so that both resources work in parallel:
+//
+//   gsl_host_pack_labels   HOST helper (no device work): int32 maps -> uint8 codes, row-major, on
+//                          n_threads host threads; also reports the value range it saw
+//   gsl_tile_codes         device: row-major uint8 codes -> the tiled packed layout of
+//                          lift_internal.cuh (what gsl_pack_labels produces from int32 maps)
+//
+// The votes themselves are computed on the device either way; this only changes which side turns
+// an int32 pixel into a code before it crosses the bus.
+#include <limits.h>
+#include <string.h>
+
+#include <thread>
+#include <vector>
+
+#include "common.cuh"
+#include "lift_internal.cuh"
+
+namespace {
+
+void narrow_range(const int32_t *in, uint8_t *out, int64_t n, int label_min, int n_classes, int *bad, int *lo_out, int *hi_out)
+{
+    int b = 0, lo = INT_MAX, hi = INT_MIN;
+    for (int64_t i = 0; i < n; ++i) {
+        const int v = in[i];
+        const unsigned c = (unsigned)(v - label_min);
+        b |= c >= (unsigned)n_classes;
+        lo = v < lo ? v : lo;
+        hi = v > hi ? v : hi;
+        out[i] = (uint8_t)(c < (unsigned)n_classes ? c + 1u : 0u);
+    }
+    *bad |= b;
+    if (lo < *lo_out) *lo_out = lo;
+    if (hi > *hi_out) *hi_out = hi;
+}
+
+}  // namespace
+
+// maps[m] = host pointer to n_px[m] int32 values; codes of map m are written at out + sum(n_px[0..m)).
+// minmax[2] (host, in/out): running min and max of the values seen.  *bad (host, out): 1 if a value
+// fell outside [label_min, label_min + n_classes) (its code is 0).
+extern "C" int gsl_host_pack_labels(const int32_t *const *maps, const int64_t *n_px, int n_maps, int label_min,
+                                    int n_classes, uint8_t *out, int n_threads, int *minmax, int *bad)
+{
+    if (n_maps < 0 || (n_maps > 0 && (!maps || !n_px || !out)) || !minmax || !bad)
+        return gsl::fail(GSL_EINVAL, "gsl_host_pack_labels: null pointer or negative count");
+    if (n_classes < 1 || n_classes > GSL_MAX_CODES) return gsl::fail(GSL_EINVAL, "gsl_host_pack_labels: n_classes %d not in [1, %d]", n_classes, GSL_MAX_CODES);
+    std::vector<int64_t> start((size_t)n_maps + 1, 0);
+    for (int m = 0; m < n_maps; ++m) {
+        if (n_px[m] < 0 || (n_px[m] > 0 && !maps[m])) return gsl::fail(GSL_EINVAL, "gsl_host_pack_labels: map %d is null or has a negative size", m);
+        start[(size_t)m + 1] = start[(size_t)m] + n_px[m];
+    }
+    const int64_t total = start[(size_t)n_maps];
+    *bad = 0;
+    if (total == 0) return GSL_OK;
+    if (n_threads < 1) n_threads = (int)std::thread::hardware_concurrency();
+    if (n_threads < 1) n_threads = 1;
+    if ((int64_t)n_threads > total / 65536 + 1) n_threads = (int)(total / 65536 + 1);
+    std::vector<int> t_bad((size_t)n_threads, 0), t_lo((size_t)n_threads, INT_MAX), t_hi((size_t)n_threads, INT_MIN);
+    auto work = [&](int t) {
+        const int64_t a = total * t / n_threads, b = total * (t + 1) / n_threads;
+        int m = 0;
+        while (start[(size_t)m + 1] <= a) ++m;
+        for (int64_t at = a; at < b;) {
+            const int64_t end = start[(size_t)m + 1] < b ? start[(size_t)m + 1] : b;
+            narrow_range(maps[m] + (at - start[(size_t)m]), out + at, end - at, label_min, n_classes,
+                         &t_bad[(size_t)t], &t_lo[(size_t)t], &t_hi[(size_t)t]);
+            at = end;
+            ++m;
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_threads; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto &th : pool) th.join();
+    for (int t = 0; t < n_threads; ++t) {
+        *bad |= t_bad[(size_t)t];
+        if (t_lo[(size_t)t] < minmax[0]) minmax[0] = t_lo[(size_t)t];
+        if (t_hi[(size_t)t] > minmax[1]) minmax[1] = t_hi[(size_t)t];
+    }
+    return GSL_OK;
+}
+
+namespace gsl {
+
+// One thread per 16-byte tile row of the output (same mapping as pack_labels_kernel).
+__global__ void __launch_bounds__(256)
+tile_codes_kernel(const uint8_t *__restrict__ codes, uint8_t *__restrict__ packed, int n_maps, int seg_w, int seg_h,
+                  uint32_t tiles_x, uint32_t tiles_y, int vec_ok)
+{
+    const int64_t rows_per_map = (int64_t)tiles_x * tiles_y * 8;
+    const int64_t total = rows_per_map * n_maps;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int64_t m = i / rows_per_map;
+        const uint32_t rem = (uint32_t)(i - m * rows_per_map);
+        const uint32_t tile = rem >> 3, r = rem & 7u;
+        const uint32_t ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        const int y = (int)(ty * 8 + r) - 8, x0 = (int)(tx * 16) - 16;
+        uint4 w = make_uint4(0u, 0u, 0u, 0u);
+        if (y >= 0 && y < seg_h && x0 >= 0 && x0 < seg_w) {
+            const uint8_t *src = codes + (m * seg_h + y) * (int64_t)seg_w + x0;
+            if (vec_ok && x0 + 16 <= seg_w) {
+                w = __ldcs(reinterpret_cast<const uint4 *>(src));
+            } else {
+                uint32_t v[4] = {0u, 0u, 0u, 0u};
+                for (int j = 0; j < 16; ++j)
+                    if (x0 + j < seg_w) v[j >> 2] |= (uint32_t)src[j] << (8 * (j & 3));
+                w = make_uint4(v[0], v[1], v[2], v[3]);
+            }
+        }
+        reinterpret_cast<uint4 *>(packed)[i] = w;
+    }
+}
+
+}  // namespace gsl
+
+extern "C" int gsl_tile_codes(const uint8_t *codes, int n_maps, int seg_w, int seg_h, uint8_t *packed, void *stream)
+{
+    using namespace gsl;
+    if (n_maps < 0 || seg_w < 1 || seg_h < 1) return fail(GSL_EINVAL, "gsl_tile_codes: negative count or empty map shape");
+    if (n_maps == 0) return GSL_OK;
+    if (!codes || !packed) return fail(GSL_EINVAL, "gsl_tile_codes: null pointer");
+    if ((uintptr_t)packed & 15) return fail(GSL_EINVAL, "gsl_tile_codes: packed must be 16-byte aligned");
+    if (packed_map_bytes(seg_w, seg_h) > 0x7fffffffLL) return fail(GSL_EINVAL, "gsl_tile_codes: map of %d x %d exceeds 2^31 packed bytes", seg_w, seg_h);
+    const uint32_t tx = map_tiles_x(seg_w), ty = map_tiles_y(seg_h);
+    const int64_t rows = (int64_t)tx * ty * 8 * n_maps;
+    int64_t blocks = (rows + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    const int vec_ok = ((uintptr_t)codes & 15) == 0 && (seg_w & 15) == 0;      // every 16-pixel run starts 16-byte aligned
+    tile_codes_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(codes, packed, n_maps, seg_w, seg_h, tx, ty, vec_ok);
+    GSL_LAUNCH_CHECK("tile_codes_kernel");
+    return GSL_OK;
+}

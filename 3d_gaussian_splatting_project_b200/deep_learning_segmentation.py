@@ -164,16 +164,61 @@ def _stage_maps(seg_maps, shapes, device, label_min, n_classes):
 
 
 _copy_streams = {}
+_pinned_codes = {}                 # pinned uint8 staging for host-narrowed views, by size
+_host_stage = {"px_per_s": None, "fixed_s": 0.008}   # calibrated by use: host narrowing rate (pixels per second, all
+                                                      # threads, with the DMA engine running) and the other host time of a call
+_PCIE_BYTES_PER_S = 54e9           # pinned host -> device copy rate of a PCIe 5 x16 link (profiles/probes/h2d_probe.py)
+
+
+def _host_fraction(seg_maps, n_px):
+    """Share of the views whose maps are narrowed to 1-byte codes on the host before they cross
+    the bus.  The DMA engine moves 4 bytes per pixel for the others meanwhile; with P pixels in all,
+    tp = bus time per byte, th = host time per pixel and c = the other host work of the call
+    (enqueueing, the view table), both sides finish together when
+        c + f P th = P tp (4 - 3 f)   =>   f = (4 P tp - c) / (P (th + 3 tp)).
+    GSLIFT_HOST_STAGE=<fraction> fixes it (0 = all maps cross as int32)."""
+    if any(isinstance(m, torch.Tensor) and m.is_cuda for m in seg_maps):
+        return 0.0
+    env = os.environ.get("GSLIFT_HOST_STAGE")
+    if env is not None:
+        return min(max(float(env), 0.0), 1.0)
+    cores = os.cpu_count() or 1
+    if cores < 8:
+        return 0.0
+    rate = _host_stage["px_per_s"] or 0.9e9 * cores
+    tp, th, c = 1.0 / _PCIE_BYTES_PER_S, 1.0 / rate, _host_stage["fixed_s"]
+    if n_px <= 0:
+        return 0.0
+    return min(max((4 * n_px * tp - c) / (n_px * (th + 3 * tp)), 0.0), 0.85)
+
+
+def _host_ptr(m):
+    """(address, keep-alive) of a host int32 map, converting only if it is not int32 / contiguous."""
+    if isinstance(m, torch.Tensor):
+        t = m if (m.dtype == torch.int32 and m.is_contiguous()) else m.to(torch.int32).contiguous()
+        return t.data_ptr(), t
+    arr = m if (isinstance(m, np.ndarray) and m.dtype == np.int32 and m.flags.c_contiguous) else np.ascontiguousarray(m, np.int32)
+    return arr.ctypes.data, arr
 
 
 def _lift_pipelined(positions, cameras, image_sizes, seg_maps, shapes, device):
-    """One-process fast path of lift_labels: the maps are uploaded 16 views at a time on a copy
-    stream while the compute stream packs and sweeps the previous 16 (gsl_lift_prepare +
-    gsl_lift_gather_range), so everything but the last window hides behind the PCIe transfer and
-    only two 16-view staging buffers exist on the device.  The first uploads are enqueued before
-    anything else happens on the host (the view table of 300 cameras takes milliseconds of NumPy),
-    because the PCIe transfer is what the call waits for.  Codes are label + 2 (label_min = -1);
-    returns None when the labels do not fit that window and the caller must take the general path."""
+    """One-process fast path of lift_labels from HOST maps, organised around the PCIe transfer,
+    which is what such a call waits for:
+
+      * the first windows of 16 views cross the bus as int32, two staging buffers in flight on a
+        copy stream, and are packed on the device (gsl_pack_labels);
+      * the remaining windows are narrowed to 1-byte codes by the host cores meanwhile
+        (gsl_host_pack_labels), cross as uint8 behind the int32 windows, and are tiled on the
+        device (gsl_tile_codes);
+      * every window is swept as soon as its packed maps are resident (gsl_lift_prepare once, then
+        gsl_lift_gather_range per window / batch), so only the last sweep and the majority are not
+        hidden behind the transfer.
+
+    The first uploads are enqueued before anything else happens on the host.  Codes are label + 2
+    (label_min = -1); returns None when the labels do not fit that window and the caller must take
+    the general path."""
+    import ctypes
+    import time
     from ._native import check, lib
     L = lib()
     V = len(seg_maps)
@@ -187,10 +232,12 @@ def _lift_pipelined(positions, cameras, image_sizes, seg_maps, shapes, device):
     copy = _copy_streams[key]
     CH = 16
     chunks = list(range(0, V, CH))
-    chunk_px = max(int(starts[min(v0 + CH, V)] - starts[v0]) for v0 in chunks)
+    n_host = int(round(_host_fraction(seg_maps, int(starts[-1])) * len(chunks)))
+    n_dev = len(chunks) - n_host                                 # windows [0, n_dev) cross as int32
+    chunk_px = max([int(starts[min(v0 + CH, V)] - starts[v0]) for v0 in chunks[:n_dev]] + [1])
     slots = [torch.empty(chunk_px, dtype=torch.int32, device=device) for _ in range(2)]
     slot_free = [None, None]
-    ready = [None] * len(chunks)
+    ready = [None] * n_dev
 
     def upload(ci):
         v0 = chunks[ci]
@@ -199,25 +246,52 @@ def _lift_pipelined(positions, cameras, image_sizes, seg_maps, shapes, device):
         with torch.cuda.stream(copy):
             if slot_free[ci % 2] is not None:
                 copy.wait_event(slot_free[ci % 2])
-            off = 0
-            for v in range(v0, v1):
+            off, v = 0, v0
+            while v < v1:
                 m = seg_maps[v]
                 src = m if isinstance(m, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(m, np.int32))
-                buf[off:off + sizes[v]].copy_(src.reshape(-1), non_blocking=True)
-                off += sizes[v]
+                n, last = sizes[v], v
+                # maps that lie back to back in one host allocation (slices of one big pinned tensor)
+                # cross in a single copy
+                if src.dtype == torch.int32 and src.is_contiguous() and not src.is_cuda:
+                    while last + 1 < v1:
+                        nxt = seg_maps[last + 1]
+                        if not (isinstance(nxt, torch.Tensor) and nxt.dtype == torch.int32 and nxt.is_contiguous() and not nxt.is_cuda
+                                and nxt.untyped_storage().data_ptr() == src.untyped_storage().data_ptr()
+                                and nxt.storage_offset() == src.storage_offset() + n):
+                            break
+                        last += 1
+                        n += sizes[last]
+                    flat = torch.as_strided(src, (n,), (1,), src.storage_offset())
+                else:
+                    flat = src.reshape(-1)
+                buf[off:off + n].copy_(flat, non_blocking=True)
+                off += n
+                v = last + 1
             ready[ci] = torch.cuda.Event()
             ready[ci].record(copy)
         return off
 
+    def pack_runs(fn, src_ptr, elem, v0, v1):
+        """fn = gsl_pack_labels / gsl_tile_codes over the runs of equal shapes of views [v0, v1)."""
+        v = v0
+        while v < v1:
+            n = 1
+            while v + n < v1 and shapes[v + n] == shapes[v]:
+                n += 1
+            yield fn, src_ptr + elem * int(starts[v] - starts[v0]), n, shapes[v][1], shapes[v][0], int(pstarts[v])
+            v += n
+
     trace = os.environ.get("GSLIFT_TRACE") == "1"               # phase timings of this call on stderr
+    t_call0 = time.perf_counter()
     with torch.cuda.device(device):
         if trace:
-            import sys, time
+            import sys
             t_host0 = time.perf_counter()
-            print(f"[gslift trace] pipeline starts at {t_host0:.6f}", file=sys.stderr)
+            print(f"[gslift trace] pipeline starts at {t_host0:.6f}; {n_dev} windows as int32, {n_host} narrowed on the host", file=sys.stderr)
             ev0 = torch.cuda.Event(enable_timing=True); ev0.record(main)
-        n_px = [0] * len(chunks)
-        for ci in range(min(2, len(chunks))):                   # the transfer starts now
+        n_px = [0] * n_dev
+        for ci in range(min(2, n_dev)):                          # the transfer starts now
             n_px[ci] = upload(ci)
         pos = positions if isinstance(positions, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(positions, np.float32))
         pos = pos.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
@@ -229,39 +303,76 @@ def _lift_pipelined(positions, cameras, image_sizes, seg_maps, shapes, device):
         err = torch.zeros(1, dtype=torch.int32, device=device)
         vptr = views.ctypes.data
         check(L.gsl_lift_prepare(pos.data_ptr(), N, vptr, V, ws.data_ptr(), ws.numel(), main.cuda_stream))
-        for ci, v0 in enumerate(chunks):
+        # ---- windows that cross as int32: everything below is enqueued without waiting
+        for ci in range(n_dev):
+            v0 = chunks[ci]
             v1 = min(v0 + CH, V)
             buf = slots[ci % 2]
             main.wait_event(ready[ci])
             check(L.gsl_label_range(buf.data_ptr(), n_px[ci], minmax.data_ptr(), main.cuda_stream))
-            v = v0
-            while v < v1:                                # one pack launch per run of equal shapes
-                n = 1
-                while v + n < v1 and shapes[v + n] == shapes[v]:
-                    n += 1
-                check(L.gsl_pack_labels(buf.data_ptr() + 4 * int(starts[v] - starts[v0]), n, shapes[v][1], shapes[v][0],
-                                        packed.data_ptr() + int(pstarts[v]), -1, 255, err.data_ptr(), main.cuda_stream))
-                v += n
+            for _, src, n, w, h, dst in pack_runs(None, buf.data_ptr(), 4, v0, v1):
+                check(L.gsl_pack_labels(src, n, w, h, packed.data_ptr() + dst, -1, 255, err.data_ptr(), main.cuda_stream))
             slot_free[ci % 2] = torch.cuda.Event()
             slot_free[ci % 2].record(main)
-            if ci + 2 < len(chunks):
+            if ci + 2 < n_dev:
                 n_px[ci + 2] = upload(ci + 2)            # refills the slot just packed
             check(L.gsl_lift_gather_range(pos.data_ptr(), N, vptr, V, v0, v1, packed.data_ptr(), None, 0.0, 0,
                                           ws.data_ptr(), ws.numel(), main.cuda_stream))
+        # ---- windows narrowed on the host, a few at a time, while the DMA engine is busy with the above
+        host_mm = (ctypes.c_int * 2)(2**31 - 1, -2**31)
+        if n_host:
+            hv0 = chunks[n_dev]
+            host_px = int(starts[V] - starts[hv0])
+            if _pinned_codes.get("n", 0) < host_px:
+                t_alloc = time.perf_counter()
+                _pinned_codes["buf"] = torch.empty(host_px, dtype=torch.uint8, pin_memory=True)
+                _pinned_codes["n"] = host_px
+                t_call0 += time.perf_counter() - t_alloc         # a one-time cost, not part of the calibration
+            pinned = _pinned_codes["buf"]
+            codes = torch.empty(host_px, dtype=torch.uint8, device=device)
+            bad = ctypes.c_int(0)
+            HB = 2                                               # windows per host batch
+            t_narrow, px_narrow = 0.0, 0
+            for b0 in range(n_dev, len(chunks), HB):
+                vb0 = chunks[b0]
+                vb1 = min(chunks[min(b0 + HB, len(chunks)) - 1] + CH, V)
+                keep = [_host_ptr(seg_maps[v]) for v in range(vb0, vb1)]
+                ptrs = (ctypes.c_void_p * len(keep))(*[k[0] for k in keep])
+                npx = (ctypes.c_int64 * len(keep))(*[sizes[v] for v in range(vb0, vb1)])
+                off0, off1 = int(starts[vb0] - starts[hv0]), int(starts[vb1] - starts[hv0])
+                t0 = time.perf_counter()
+                check(L.gsl_host_pack_labels(ptrs, npx, len(keep), -1, 255, pinned.data_ptr() + off0, 0, host_mm, ctypes.byref(bad)))
+                t_narrow += time.perf_counter() - t0
+                px_narrow += off1 - off0
+                with torch.cuda.stream(copy):
+                    codes[off0:off1].copy_(pinned[off0:off1], non_blocking=True)
+                    landed = torch.cuda.Event()
+                    landed.record(copy)
+                main.wait_event(landed)
+                for _, src, n, w, h, dst in pack_runs(None, codes.data_ptr() + off0, 1, vb0, vb1):
+                    check(L.gsl_tile_codes(src, n, w, h, packed.data_ptr() + dst, main.cuda_stream))
+                check(L.gsl_lift_gather_range(pos.data_ptr(), N, vptr, V, vb0, vb1, packed.data_ptr(), None, 0.0, 0,
+                                              ws.data_ptr(), ws.numel(), main.cuda_stream))
+            if t_narrow > 0:
+                _host_stage["px_per_s"] = px_narrow / t_narrow
+                # the other host work of this call; first calls also pay allocations, hence the cap
+                _host_stage["fixed_s"] = min(max(time.perf_counter() - t_call0 - t_narrow, 0.0), 0.015)
         if trace:
             t_host1 = time.perf_counter()
             ev_up = torch.cuda.Event(enable_timing=True); ev_up.record(copy)
             ev_sw = torch.cuda.Event(enable_timing=True); ev_sw.record(main)
         lo, hi = (int(x) for x in minmax.tolist())           # synchronises: every copy has been consumed
+        lo, hi = min(lo, int(host_mm[0])), max(hi, int(host_mm[1]))
         if lo < -1 or hi > 253:
             return None
         labels = torch.empty(N, dtype=torch.int32, device=device)
         check(L.gsl_lift_majority(N, V, -1, max(hi + 2, 1), labels.data_ptr(), ws.data_ptr(), ws.numel(), main.cuda_stream))
         if trace:
-            import sys
             ev_mj = torch.cuda.Event(enable_timing=True); ev_mj.record(main)
             ev_mj.synchronize()
-            print(f"[gslift trace] majority done at {time.perf_counter():.6f} | host enqueue {1e3 * (t_host1 - t_host0):.2f} ms | uploads done +{ev0.elapsed_time(ev_up):.2f} ms | "
+            rate = _host_stage["px_per_s"]
+            print(f"[gslift trace] majority done at {time.perf_counter():.6f} | host enqueue + narrowing {1e3 * (t_host1 - t_host0):.2f} ms"
+                  f" ({'%.1f' % (rate / 1e9) if rate else '-'} Gpx/s) | uploads done +{ev0.elapsed_time(ev_up):.2f} ms | "
                   f"last sweep done +{ev0.elapsed_time(ev_sw):.2f} ms | majority done +{ev0.elapsed_time(ev_mj):.2f} ms", file=sys.stderr)
     return labels
 

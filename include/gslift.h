@@ -90,6 +90,20 @@ int64_t gsl_packed_map_bytes(int seg_w, int seg_h);
 int gsl_pack_labels(const int32_t *maps, int n_maps, int seg_w, int seg_h, uint8_t *packed,
                     int label_min, int n_classes, int *d_err, void *stream);
 
+/*
+ * Hybrid staging from HOST int32 maps (the PCIe transfer of 4 bytes per pixel is what a call from
+ * host maps waits for): gsl_host_pack_labels is a HOST-side helper (no device work) that narrows
+ * maps to the same uint8 codes on n_threads host threads (0 = all), so that some views can cross
+ * the bus as 1 byte per pixel while the DMA engine moves the others as int32; gsl_tile_codes turns
+ * such row-major codes (device) into the packed layout gsl_pack_labels produces.
+ *   maps[m]   HOST pointer to the n_px[m] int32 values of map m; its codes go to out + sum(n_px[0..m))
+ *   minmax    HOST int[2], in/out: running min / max of the values seen
+ *   bad       HOST int, out: 1 if a value fell outside [label_min, label_min + n_classes) (code 0)
+ */
+int gsl_host_pack_labels(const int32_t *const *maps, const int64_t *n_px, int n_maps, int label_min,
+                         int n_classes, uint8_t *out, int n_threads, int *minmax, int *bad);
+int gsl_tile_codes(const uint8_t *codes, int n_maps, int seg_w, int seg_h, uint8_t *packed, void *stream);
+
 /* Device min/max of an int32 buffer into d_minmax[2] (caller initialises to INT_MAX,
  * INT_MIN); lets the host choose label_min / n_classes without a CPU pass. */
 int gsl_label_range(const int32_t *maps, int64_t n_px, int *d_minmax, void *stream);

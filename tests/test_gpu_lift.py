@@ -286,3 +286,33 @@ def test_float32_screening_hard_cases_against_oracle(oracle):
     flips = compare(got, want, near)
     print(f"[screening edges] visible pairs {vis}, near-boundary Gaussians {int(near.sum())}, flips {flips}")
     assert flips == 0
+
+
+@pytest.mark.parametrize("fraction", ["0", "0.5", "1"])
+def test_hybrid_staging_host_narrowed_views_give_the_same_labels(oracle, monkeypatch, fraction):
+    """lift_labels from host maps: views narrowed to 1-byte codes on the host (gsl_host_pack_labels
+    + gsl_tile_codes) and views that cross as int32 (gsl_pack_labels) must give the oracle's labels
+    for every split, with ragged map shapes (scalar tile path), int64 / non-contiguous NumPy maps,
+    CPU tensors, and 40 views (3 windows, the last one partial)."""
+    dls, scene = pkg("deep_learning_segmentation"), pkg("scene")
+    v = 40
+    cams = scene.lookat_cameras(v, width=320, height=200, seed=41)
+    pos = scene.gaussian_cloud(30_000, 1.5, seed=42)
+    shapes = [(200, 320) if i % 3 else (111, 203) for i in range(v)]
+    sizes = [(320, 200) if i % 3 else (301, 155) for i in range(v)]
+    base = [scene.block_label_map(h, w, 4, -1, 149, 800 + i) for i, (h, w) in enumerate(shapes)]
+    maps = []
+    for i, m in enumerate(base):
+        if i % 4 == 1:
+            maps.append(m.astype(np.int64))                      # converted on the host
+        elif i % 4 == 2:
+            maps.append(np.asfortranarray(m))                    # not C-contiguous
+        elif i % 4 == 3:
+            maps.append(torch.from_numpy(m.copy()))              # CPU tensor
+        else:
+            maps.append(m)
+    flat = np.concatenate([m.reshape(-1) for m in base])
+    want, _, _ = oracle.lift_votes(pos, oracle.make_views(cams, shapes, sizes), flat)
+    monkeypatch.setenv("GSLIFT_HOST_STAGE", fraction)
+    got = dls.lift_labels(pos, cams, maps, sizes)
+    compare(got, want)
