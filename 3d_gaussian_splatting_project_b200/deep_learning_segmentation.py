@@ -164,6 +164,7 @@ def _stage_maps(seg_maps, shapes, device, label_min, n_classes):
 
 
 _copy_streams = {}
+last_call_stats = {}               # bytes lift_labels moved over PCIe in its last call (this process)
 _pinned_codes = {}                 # pinned uint8 staging for host-narrowed views, by size
 _host_stage = {"px_per_s": None, "fixed_s": 0.008}   # calibrated by use: host narrowing rate (pixels per second, all
                                                       # threads, with the DMA engine running) and the other host time of a call
@@ -357,6 +358,9 @@ def _lift_pipelined(positions, cameras, image_sizes, seg_maps, shapes, device):
                 _host_stage["px_per_s"] = px_narrow / t_narrow
                 # the other host work of this call; first calls also pay allocations, hence the cap
                 _host_stage["fixed_s"] = min(max(time.perf_counter() - t_call0 - t_narrow, 0.0), 0.015)
+        dev_px = int(starts[chunks[n_dev]] if n_dev < len(chunks) else starts[V])
+        last_call_stats.update(h2d_bytes=4 * dev_px + int(starts[V] - dev_px) + int(pos.numel()) * 4, d2h_bytes=N * 4,
+                               views_as_int32=min(n_dev * CH, V), views_narrowed_on_host=V - min(n_dev * CH, V))
         if trace:
             t_host1 = time.perf_counter()
             ev_up = torch.cuda.Event(enable_timing=True); ev_up.record(copy)
@@ -404,6 +408,9 @@ def lift_labels(positions, cameras, seg_maps, image_sizes=None, device=None, wan
     pos = pos.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
     views = ops.make_views(cameras, shapes, image_sizes)
     packed, label_min, n_classes = _stage_maps(seg_maps, shapes, device, label_min, n_classes)
+    world = dist.get_world_size() if not single else 1
+    last_call_stats.update(h2d_bytes=4 * sum(h * w for h, w in shapes) // world + int(pos.numel()) * 4, d2h_bytes=int(pos.shape[0]) * 4,
+                           views_as_int32=len(shapes), views_narrowed_on_host=0)
     res = ops.lift_votes(pos, views, packed, label_min, n_classes, want_near=want_near, near_eps=near_eps)
     if want_near:
         return _to_host(res[0]), _to_host(res[1])

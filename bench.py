@@ -15,7 +15,9 @@ gsl_lift_gather_range + gsl_lift_majority) with positions and packed maps reside
 K-means iterations (gsl_kmeans_step_exchange: assignment + sums, then reduction fused with the
 cross-rank exchange and the update) are timed the same way and reported under "kmeans".  `e2e` is the same lifting through the public Python entry point
 (deep_learning_segmentation.lift_labels) with pinned HOST inputs: int32 maps and positions
-are copied to the device and labels copied back inside the timed region.
+go to the device (on one GPU part of the maps is narrowed to 1-byte codes by the host cores while
+the DMA engine moves the others as int32) and labels are copied back, all inside the timed region;
+`h2d_bytes_per_step` is counted from the tensors actually copied.
 
 `--impl reference` times the reference's CPU algorithm instead: the reference is pure Python
 and cannot be compiled, so this runs the oracle's C port of it (oracle/gsl_oracle.c, OpenMP,
@@ -391,9 +393,13 @@ def run_native(a):
         dt = (time.perf_counter() - t0) / steps_e
         dt = sharding.barrier_max_ms(dt * 1e3, dev) * 1e-3
         assert np.array_equal(got, labels.cpu().numpy()), "e2e labels differ from the device-resident run"
-        maps_bytes = int(maps.nbytes)                  # every view crosses PCIe once job-wide (ranks split the views)
+        # bytes that crossed PCIe in the last call, counted by lift_labels from the tensors it copied
+        # (job-wide: every rank uploads its share of the views and its own positions)
+        st = dict(dls.last_call_stats)
+        h2d = st["h2d_bytes"] * world if world > 1 else st["h2d_bytes"]
         e2e = {"value": a.gaussians * V / dt, "unit": UNIT, "ms_per_step": dt * 1e3,
-               "h2d_bytes_per_step": maps_bytes + a.gaussians * 12, "d2h_bytes_per_step": a.gaussians * 4,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": a.gaussians * 4,
+               "staging": f"{st['views_as_int32']} views cross as int32 and are packed on the device, {st['views_narrowed_on_host']} are narrowed to uint8 codes on the host cores meanwhile",
                "call": "deep_learning_segmentation.lift_labels(positions, cameras, seg_maps) with pinned host int32 maps"}
 
     # ---- CPU baseline (rank 0, N=1 only)
