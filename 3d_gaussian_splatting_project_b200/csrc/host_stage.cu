@@ -20,9 +20,8 @@
 
 namespace {
 
-void narrow_range(const int32_t *in, uint8_t *out, int64_t n, int label_min, int n_classes, int *bad, int *lo_out, int *hi_out)
+void narrow_scalar(const int32_t *in, uint8_t *out, int64_t n, int label_min, int n_classes, int &b, int &lo, int &hi)
 {
-    int b = 0, lo = INT_MAX, hi = INT_MIN;
     for (int64_t i = 0; i < n; ++i) {
         const int v = in[i];
         const unsigned c = (unsigned)(v - label_min);
@@ -31,6 +30,56 @@ void narrow_range(const int32_t *in, uint8_t *out, int64_t n, int label_min, int
         hi = v > hi ? v : hi;
         out[i] = (uint8_t)(c < (unsigned)n_classes ? c + 1u : 0u);
     }
+}
+
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+// 32 pixels per iteration: four 8 x int32 vectors -> one 32 x uint8 vector.
+__attribute__((target("avx2")))
+int64_t narrow_avx2(const int32_t *in, uint8_t *out, int64_t n, int label_min, int n_classes, int &b, int &lo, int &hi)
+{
+    const __m256i vmin = _mm256_set1_epi32(label_min), one = _mm256_set1_epi32(1);
+    const __m256i sign = _mm256_set1_epi32((int)0x80000000u);
+    const __m256i lim = _mm256_set1_epi32((int)((unsigned)n_classes ^ 0x80000000u));     // unsigned c < n  <=>  (c ^ sign) < (n ^ sign) signed
+    const __m256i fix = _mm256_setr_epi32(0, 4, 1, 5, 2, 6, 3, 7);
+    __m256i vlo = _mm256_set1_epi32(lo), vhi = _mm256_set1_epi32(hi), vbad = _mm256_setzero_si256();
+    int64_t i = 0;
+    for (; i + 32 <= n; i += 32) {
+        __m256i code[4];
+        for (int j = 0; j < 4; ++j) {
+            const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(in + i + 8 * j));
+            vlo = _mm256_min_epi32(vlo, v);
+            vhi = _mm256_max_epi32(vhi, v);
+            const __m256i c = _mm256_sub_epi32(v, vmin);
+            const __m256i ok = _mm256_cmpgt_epi32(lim, _mm256_xor_si256(c, sign));
+            vbad = _mm256_or_si256(vbad, _mm256_andnot_si256(ok, one));
+            code[j] = _mm256_and_si256(_mm256_add_epi32(c, one), ok);
+        }
+        const __m256i ab = _mm256_packus_epi32(code[0], code[1]), cd = _mm256_packus_epi32(code[2], code[3]);
+        const __m256i bytes = _mm256_permutevar8x32_epi32(_mm256_packus_epi16(ab, cd), fix);
+        _mm256_storeu_si256(reinterpret_cast<__m256i *>(out + i), bytes);
+    }
+    alignas(32) int t[8];
+    _mm256_store_si256(reinterpret_cast<__m256i *>(t), vlo);
+    for (int j = 0; j < 8; ++j) lo = t[j] < lo ? t[j] : lo;
+    _mm256_store_si256(reinterpret_cast<__m256i *>(t), vhi);
+    for (int j = 0; j < 8; ++j) hi = t[j] > hi ? t[j] : hi;
+    _mm256_store_si256(reinterpret_cast<__m256i *>(t), vbad);
+    for (int j = 0; j < 8; ++j) b |= t[j];
+    return i;
+}
+#define GSL_HAVE_AVX2 1
+#endif
+
+void narrow_range(const int32_t *in, uint8_t *out, int64_t n, int label_min, int n_classes, int *bad, int *lo_out, int *hi_out)
+{
+    int b = 0, lo = INT_MAX, hi = INT_MIN;
+    int64_t done = 0;
+#ifdef GSL_HAVE_AVX2
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (avx2) done = narrow_avx2(in, out, n, label_min, n_classes, b, lo, hi);
+#endif
+    narrow_scalar(in + done, out + done, n - done, label_min, n_classes, b, lo, hi);
     *bad |= b;
     if (lo < *lo_out) *lo_out = lo;
     if (hi > *hi_out) *hi_out = hi;
