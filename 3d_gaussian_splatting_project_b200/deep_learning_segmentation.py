@@ -171,6 +171,14 @@ _host_stage = {"px_per_s": None, "fixed_s": 0.008}   # calibrated by use: host n
 _PCIE_BYTES_PER_S = 54e9           # pinned host -> device copy rate of a PCIe 5 x16 link (profiles/probes/h2d_probe.py)
 
 
+def _host_cores():
+    """Host cores this process may run on (affinity / cgroup aware where the platform tells)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        return os.cpu_count() or 1
+
+
 def _host_fraction(seg_maps, n_px):
     """Share of the views whose maps are narrowed to 1-byte codes on the host before they cross
     the bus.  The DMA engine moves 4 bytes per pixel for the others meanwhile; with P pixels in all,
@@ -183,7 +191,7 @@ def _host_fraction(seg_maps, n_px):
     env = os.environ.get("GSLIFT_HOST_STAGE")
     if env is not None:
         return min(max(float(env), 0.0), 1.0)
-    cores = os.cpu_count() or 1
+    cores = _host_cores()
     if cores < 8:
         return 0.0
     rate = _host_stage["px_per_s"] or 0.9e9 * cores
@@ -342,7 +350,7 @@ def _lift_pipelined(positions, cameras, image_sizes, seg_maps, shapes, device):
                 npx = (ctypes.c_int64 * len(keep))(*[sizes[v] for v in range(vb0, vb1)])
                 off0, off1 = int(starts[vb0] - starts[hv0]), int(starts[vb1] - starts[hv0])
                 t0 = time.perf_counter()
-                check(L.gsl_host_pack_labels(ptrs, npx, len(keep), -1, 255, pinned.data_ptr() + off0, 0, host_mm, ctypes.byref(bad)))
+                check(L.gsl_host_pack_labels(ptrs, npx, len(keep), -1, 255, pinned.data_ptr() + off0, _host_cores(), host_mm, ctypes.byref(bad)))
                 t_narrow += time.perf_counter() - t0
                 px_narrow += off1 - off0
                 with torch.cuda.stream(copy):
