@@ -69,22 +69,31 @@ def make_views(cameras, map_shapes, image_sizes=None) -> np.ndarray:
     same rounding the reference would see on this host.  Packed maps are laid out back to back
     (packed_offsets).
     """
-    views = np.zeros(len(cameras), VIEW_DTYPE)
-    offs = packed_offsets([tuple(int(s) for s in sh) for sh in map_shapes]) if len(cameras) else np.zeros(1, np.int64)
-    for v, cam in enumerate(cameras):
-        R = np.array(cam["rotation"])
-        p = np.array(cam["position"])
-        seg_h, seg_w = (int(s) for s in map_shapes[v])
-        ow, oh = (seg_w, seg_h) if image_sizes is None else (int(s) for s in image_sizes[v])
-        rec = views[v]
-        rec["R"] = np.asarray(R, np.float64).reshape(9)
-        rec["t"] = -R @ p
-        rec["fx"], rec["fy"] = cam["fx"], cam["fy"]
-        rec["half_w"], rec["half_h"] = cam["width"] / 2, cam["height"] / 2
-        rec["width"], rec["height"] = cam["width"], cam["height"]
-        rec["scale_x"], rec["scale_y"] = seg_w / ow, seg_h / oh
-        rec["seg_w"], rec["seg_h"] = seg_w, seg_h
-        rec["map_offset"] = int(offs[v])
+    n = len(cameras)
+    views = np.zeros(n, VIEW_DTYPE)
+    if n == 0:
+        return views
+    shapes = np.array([[int(s) for s in sh] for sh in map_shapes], dtype=np.int64).reshape(n, 2)      # (seg_h, seg_w)
+    images = shapes[:, ::-1] if image_sizes is None else np.array([[int(s) for s in sz] for sz in image_sizes], dtype=np.int64)
+    R = np.array([cam["rotation"] for cam in cameras])
+    p = np.array([cam["position"] for cam in cameras])
+    if R.dtype != np.float64 or R.shape != (n, 3, 3) or p.dtype != np.float64 or p.shape != (n, 3):
+        R = np.array([np.array(cam["rotation"], dtype=np.float64) for cam in cameras]).reshape(n, 3, 3)
+        p = np.array([np.array(cam["position"], dtype=np.float64) for cam in cameras]).reshape(n, 3)
+    views["R"] = R.reshape(n, 9)
+    t = views["t"]
+    for v in range(n):                       # one 3x3 matrix-vector product per camera, as the reference does it
+        t[v] = -R[v] @ p[v]
+    width = np.array([cam["width"] for cam in cameras])
+    height = np.array([cam["height"] for cam in cameras])
+    views["fx"] = [cam["fx"] for cam in cameras]
+    views["fy"] = [cam["fy"] for cam in cameras]
+    views["half_w"], views["half_h"] = width / 2, height / 2
+    views["width"], views["height"] = width, height
+    views["scale_x"] = shapes[:, 1] / images[:, 0]
+    views["scale_y"] = shapes[:, 0] / images[:, 1]
+    views["seg_w"], views["seg_h"] = shapes[:, 1], shapes[:, 0]
+    views["map_offset"] = packed_offsets([(int(h), int(w)) for h, w in shapes])[:-1]
     return views
 
 
