@@ -24,7 +24,7 @@ void narrow_scalar(const int32_t *in, uint8_t *out, int64_t n, int label_min, in
 {
     for (int64_t i = 0; i < n; ++i) {
         const int v = in[i];
-        const unsigned c = (unsigned)(v - label_min);
+        const unsigned c = (unsigned)v - (unsigned)label_min;      // wraps, like the vector path
         b |= c >= (unsigned)n_classes;
         lo = v < lo ? v : lo;
         hi = v > hi ? v : hi;

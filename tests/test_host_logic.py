@@ -148,3 +148,40 @@ def test_sharding_world_size_2_gloo(tmp_path):
                          capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert out.stdout.count("ok") == 2
+
+
+def test_host_label_narrowing_matches_numpy():
+    """gsl_host_pack_labels (host-side staging helper, no device): codes, value range and the
+    out-of-range flag against NumPy, over sizes around the 32-pixel vector width, several maps per
+    call and thread ranges that cross map boundaries."""
+    import ctypes
+    L = pkg("_native").lib()
+    rng = np.random.default_rng(0)
+
+    def run(maps, label_min, n_classes, n_threads):
+        tot = sum(m.size for m in maps)
+        out = np.full(tot + 64, 0xAB, np.uint8)                   # guard bytes behind the output
+        ptrs = (ctypes.c_void_p * len(maps))(*[m.ctypes.data for m in maps])
+        npx = (ctypes.c_int64 * len(maps))(*[m.size for m in maps])
+        mm = (ctypes.c_int * 2)(2**31 - 1, -2**31)
+        bad = ctypes.c_int(0)
+        assert L.gsl_host_pack_labels(ptrs, npx, len(maps), label_min, n_classes, out.ctypes.data, n_threads, mm, ctypes.byref(bad)) == 0
+        assert (out[tot:] == 0xAB).all(), "wrote past the end"
+        return out[:tot], (mm[0], mm[1]), bad.value
+
+    for n in (0, 1, 31, 32, 33, 1000, 123457):
+        a = rng.integers(-5, 300, n).astype(np.int32)
+        got, mm, bad = run([a], -1, 255, 0)
+        c = a.astype(np.int64) + 1
+        want = np.where((c >= 0) & (c < 255), c + 1, 0).astype(np.uint8)
+        assert np.array_equal(got, want), n
+        if n:
+            assert mm == (int(a.min()), int(a.max())) and bad == int(((c < 0) | (c >= 255)).any())
+    maps = [rng.integers(-1, 150, s).astype(np.int32) for s in (70001, 5, 300000, 64, 0, 131072)]
+    for nt in (1, 3, 5, 8):
+        got, mm, bad = run(maps, -1, 151, nt)
+        assert np.array_equal(got, (np.concatenate(maps) + 2).astype(np.uint8)) and bad == 0 and mm == (-1, 149)
+    ext = np.array([-2**31, 2**31 - 1, 0, 7], np.int32)           # wrap-around of v - label_min must not alias a valid code
+    got, mm, bad = run([ext], 5, 10, 1)
+    assert got.tolist() == [0, 0, 0, 3] and bad == 1 and mm == (-2**31, 2**31 - 1)
+    assert L.gsl_host_pack_labels(None, None, 1, -1, 255, None, 0, None, None) == -1
