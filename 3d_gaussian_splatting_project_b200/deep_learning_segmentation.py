@@ -340,11 +340,17 @@ def _lift_pipelined(positions, cameras, image_sizes, seg_maps, shapes, device):
             pinned = _pinned_codes["buf"]
             codes = torch.empty(host_px, dtype=torch.uint8, device=device)
             bad = ctypes.c_int(0)
-            HB = 2                                               # windows per host batch
+            # host batches of two windows; the last two windows go one at a time, so that little is
+            # left to upload and sweep once the host is done
+            batches, b0 = [], n_dev
+            while b0 < len(chunks):
+                nb = 2 if len(chunks) - b0 > 3 else 1
+                batches.append((b0, min(b0 + nb, len(chunks))))
+                b0 += nb
             t_narrow, px_narrow = 0.0, 0
-            for b0 in range(n_dev, len(chunks), HB):
+            for b0, b1 in batches:
                 vb0 = chunks[b0]
-                vb1 = min(chunks[min(b0 + HB, len(chunks)) - 1] + CH, V)
+                vb1 = min(chunks[b1 - 1] + CH, V)
                 keep = [_host_ptr(seg_maps[v]) for v in range(vb0, vb1)]
                 ptrs = (ctypes.c_void_p * len(keep))(*[k[0] for k in keep])
                 npx = (ctypes.c_int64 * len(keep))(*[sizes[v] for v in range(vb0, vb1)])
