@@ -141,37 +141,78 @@ ordered_chain_kernel(const float *__restrict__ data, int D, const int32_t *__res
         return;
     }
     const int64_t n_batches = (n + kChainRows - 1) / kChainRows;
-    auto issue = [&](int64_t b) {               // producers: this warp's 32 rows of batch b
+    // producers: this warp's 32 rows of batch b.  The member indices of a batch are loaded one
+    // iteration before its copies are issued (load_idx -> issue): otherwise the latency of that
+    // load (~1 us) sits in front of every batch's cp.async and, through the barrier, in front of the
+    // consumer (profiles/r1/ncu_ordered_chain_r1.txt: the producers' first SHFL held 20 % of all samples).
+    auto load_idx = [&](int64_t b) -> int {
         if (w > 0 && b < n_batches) {
             const int64_t mi = b * kChainRows + (w - 1) * 32 + lane;
-            const int idx = mi < n ? members[s0 + mi] : -1;
-            float *dst = buf + ((size_t)(b % kChainRing) * kChainRows + (size_t)(w - 1) * 32) * 32 + lane;
+            return mi < n ? __ldg(members + s0 + mi) : -1;
+        }
+        return -1;
+    };
+    // per row: one broadcast shared load (the row index, parked there by the lane that fetched it),
+    // one 32 x 32 -> 64-bit multiply-add (the source address) and the copy itself -- the seven
+    // producer warps share the SM's issue slots with the consumer.  (Broadcasting the indices with
+    // shuffles compiled to a dozen instructions per row: the warp-uniform branch around them is not
+    // provably convergent, so every shuffle came with its own collective-sync scaffolding.)
+    __shared__ int idx_s[7 * 32];
+    const char *base = reinterpret_cast<const char *>(data + (live ? d : 0));
+    asm volatile("" : "+l"(base));                               // keep it in registers, do not re-derive it per row
+    const unsigned row_bytes = (unsigned)D * 4u;
+    const unsigned buf_s = (unsigned)__cvta_generic_to_shared(buf);
+    auto issue = [&](int64_t b, int idx) {
+        if (w > 0 && b < n_batches) {
+            int *mine = idx_s + (w - 1) * 32;
+            __syncwarp();                                        // the previous batch's reads of this warp's slots are done
+            mine[lane] = idx;
+            __syncwarp();
+            unsigned dst = buf_s + (((unsigned)(b % kChainRing) * kChainRows + (unsigned)(w - 1) * 32u) * 32u + (unsigned)lane) * 4u;
+            asm volatile("" : "+r"(dst));                        // one register plus an immediate per row
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int r = __shfl_sync(0xffffffffu, idx, j);
-                if (r >= 0 && live) cp_async_4(dst + j * 32, data + (size_t)r * D + d);
+            for (int j0 = 0; j0 < 32; j0 += 8) {
+                int r[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) r[j] = mine[j0 + j];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (live && r[j] >= 0)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + (unsigned)(j0 + j) * 128u), "l"(base + (size_t)(unsigned)r[j] * row_bytes) : "memory");
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    for (int p = 0; p < kChainRing - 1; ++p) issue(p);
+    for (int p = 0; p < kChainRing - 1; ++p) issue(p, load_idx(p));
+    int idx_next = load_idx(kChainRing - 1);
     float acc = -0.0f;              // (-0) + x == x for every x: same as starting from the first row
     for (int64_t b = 0; b < n_batches; ++b) {
         asm volatile("cp.async.wait_group %0;" ::"n"(kChainRing - 2) : "memory");   // my part of batch b landed
         __syncthreads();            // everyone's part landed; the consumer is done with batch b - 1
-        issue(b + kChainRing - 1);  // refills the slot batch b - 1 occupied
+        issue(b + kChainRing - 1, idx_next);    // refills the slot batch b - 1 occupied
+        idx_next = load_idx(b + kChainRing);    // in flight while the consumer adds batch b
         if (w == 0 && live) {
             const int cnt = (int)min((int64_t)kChainRows, n - b * kChainRows);
             const float *src = buf + (size_t)(b % kChainRing) * kChainRows * 32 + lane;
-            // the adds are one dependent chain (4 cycles each); the shared loads are batched 32
-            // deep so that their latency is paid once per 32 adds
+            // the adds are one dependent chain (4 cycles each); the shared loads of the NEXT 32
+            // values are issued before the 32 adds of the current ones, so the chain does not wait
+            // for shared memory inside a batch
             int i = 0;
-            for (; i + 32 <= cnt; i += 32) {
-                float x[32];
+            if (cnt >= 32) {
+                float x[32], y[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) x[j] = src[(i + j) * 32];
+                for (int j = 0; j < 32; ++j) x[j] = src[j * 32];
+                for (; i + 64 <= cnt; i += 32) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) y[j] = src[(i + 32 + j) * 32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc = __fadd_rn(acc, x[j]);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) x[j] = y[j];
+                }
 #pragma unroll
                 for (int j = 0; j < 32; ++j) acc = __fadd_rn(acc, x[j]);
+                i += 32;
             }
             for (; i < cnt; ++i) acc = __fadd_rn(acc, src[i * 32]);
         }
