@@ -9,6 +9,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgslift.so")
+ABI_VERSION = 3
 
 # Mirrors `GslView` in include/gslift.h.
 VIEW_DTYPE = np.dtype(
@@ -37,17 +38,18 @@ SIGNATURES = {
     "gsl_version": (_i32, []),
     "gsl_last_error": (ctypes.c_char_p, []),
     "gsl_device_count": (_i32, []),
+    "gsl_launch_count": (ctypes.c_ulonglong, []),
     "gsl_packed_map_bytes": (_i64, [_i32, _i32]),
     "gsl_pack_labels": (_i32, [_vp, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _vp]),
     "gsl_host_pack_labels": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _vp, _vp]),
     "gsl_tile_codes": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "gsl_label_range": (_i32, [_vp, _i64, _vp, _vp]),
     "gsl_lift_workspace_bytes": (_sz, [_i64, _i32]),
-    "gsl_lift_votes": (_i32, [_vp, _i64, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _dbl, _i32, _vp, _sz, _vp]),
-    "gsl_lift_gather": (_i32, [_vp, _i64, _vp, _i32, _vp, _vp, _dbl, _i32, _vp, _sz, _vp]),
+    "gsl_lift_votes": (_i32, [_vp, _i64, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _dbl, _vp, _sz, _vp]),
     "gsl_lift_prepare": (_i32, [_vp, _i64, _vp, _i32, _vp, _sz, _vp]),
-    "gsl_lift_gather_range": (_i32, [_vp, _i64, _vp, _i32, _i32, _i32, _vp, _vp, _dbl, _i32, _vp, _sz, _vp]),
-    "gsl_lift_majority": (_i32, [_i64, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
+    "gsl_lift_sweep": (_i32, [_vp, _i64, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "gsl_lift_merge": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp]),
+    "gsl_lift_near": (_i32, [_vp, _i64, _vp, _i32, _vp, _dbl, _vp, _sz, _vp]),
     "gsl_div_selftest": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "gsl_kmeans_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "gsl_kmeans_assign": (_i32, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _sz, _vp]),
@@ -85,8 +87,8 @@ def lib() -> ctypes.CDLL:
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        if L.gsl_version() != 2:
-            raise ImportError(f"libgslift ABI {L.gsl_version()} != 2; rebuild")
+        if L.gsl_version() != ABI_VERSION:
+            raise ImportError(f"libgslift ABI {L.gsl_version()} != {ABI_VERSION}; rebuild")
         _lib = L
     return _lib
 

@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace gsl {
@@ -25,6 +27,10 @@ int fail(int code, const char *fmt, ...)
     return code;
 }
 
+static std::atomic<unsigned long long> g_launches{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
 int sm_count()
 {
     static thread_local int cached_dev = -1, cached = 0;
@@ -44,6 +50,8 @@ int sm_count()
 extern "C" int gsl_version(void) { return GSL_ABI_VERSION; }
 
 extern "C" const char *gsl_last_error(void) { return gsl::g_err; }
+
+extern "C" unsigned long long gsl_launch_count(void) { return gsl::g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int gsl_device_count(void)
 {

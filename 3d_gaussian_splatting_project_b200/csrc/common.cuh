@@ -20,8 +20,12 @@ int fail(int code, const char *fmt, ...);
                              cudaGetErrorString(_e), __FILE__, __LINE__);                \
     } while (0)
 
+// Every kernel launch of the library passes through here; the count backs gsl_launch_count().
+void count_launch();
+
 #define GSL_LAUNCH_CHECK(name)                                                           \
     do {                                                                                 \
+        gsl::count_launch();                                                             \
         cudaError_t _e = cudaGetLastError();                                             \
         if (_e != cudaSuccess)                                                           \
             return gsl::fail(GSL_ECUDA, "launch of %s failed: %s", name,                 \

@@ -4,7 +4,7 @@
 //
 //   gsl_host_pack_labels   HOST helper (no device work): int32 maps -> uint8 codes, row-major, on
 //                          n_threads host threads; also reports the value range it saw
-//   gsl_tile_codes         device: row-major uint8 codes -> the tiled packed layout of
+//   gsl_tile_codes         device: row-major uint8 codes -> the packed strip layout of
 //                          lift_internal.cuh (what gsl_pack_labels produces from int32 maps)
 //
 // The votes themselves are computed on the device either way; this only changes which side turns
@@ -134,20 +134,24 @@ extern "C" int gsl_host_pack_labels(const int32_t *const *maps, const int64_t *n
 
 namespace gsl {
 
-// One thread per 16-byte tile row of the output (same mapping as pack_labels_kernel).
+// One thread per 16-byte row of the output, a warp = 4 adjacent strips x 8 rows (same mapping as
+// pack_labels_kernel in lift.cu): 8 runs of 64 consecutive codes in, four 128-byte lines out.
 __global__ void __launch_bounds__(256)
 tile_codes_kernel(const uint8_t *__restrict__ codes, uint8_t *__restrict__ packed, int n_maps, int seg_w, int seg_h,
-                  uint32_t tiles_x, uint32_t tiles_y, int vec_ok)
+                  uint32_t strips_x, uint32_t rows_pad, int64_t total, int vec_ok)
 {
-    const int64_t rows_per_map = (int64_t)tiles_x * tiles_y * 8;
-    const int64_t total = rows_per_map * n_maps;
+    const uint32_t groups_x = (strips_x + 3u) >> 2, groups_y = rows_pad >> 3;
+    const int64_t per_map = (int64_t)groups_x * groups_y * 32;
+    const int64_t map_rows = (int64_t)strips_x * rows_pad;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const int64_t m = i / rows_per_map;
-        const uint32_t rem = (uint32_t)(i - m * rows_per_map);
-        const uint32_t tile = rem >> 3, r = rem & 7u;
-        const uint32_t ty = tile / tiles_x, tx = tile - ty * tiles_x;
-        const int y = (int)(ty * 8 + r) - 8, x0 = (int)(tx * 16) - 16;
+        const int64_t m = i / per_map;
+        const uint32_t rem = (uint32_t)(i - m * per_map);
+        const uint32_t grp = rem >> 5, lane = rem & 31u;
+        const uint32_t gy = grp / groups_x, gx = grp - gy * groups_x;
+        const uint32_t strip = gx * 4u + (lane >> 3), row = gy * 8u + (lane & 7u);
+        if (strip >= strips_x) continue;
+        const int y = (int)row - 8, x0 = (int)(strip * 16) - 16;
         uint4 w = make_uint4(0u, 0u, 0u, 0u);
         if (y >= 0 && y < seg_h && x0 >= 0 && x0 < seg_w) {
             const uint8_t *src = codes + (m * seg_h + y) * (int64_t)seg_w + x0;
@@ -160,7 +164,7 @@ tile_codes_kernel(const uint8_t *__restrict__ codes, uint8_t *__restrict__ packe
                 w = make_uint4(v[0], v[1], v[2], v[3]);
             }
         }
-        reinterpret_cast<uint4 *>(packed)[i] = w;
+        reinterpret_cast<uint4 *>(packed)[m * map_rows + (int64_t)strip * rows_pad + row] = w;
     }
 }
 
@@ -174,13 +178,13 @@ extern "C" int gsl_tile_codes(const uint8_t *codes, int n_maps, int seg_w, int s
     if (!codes || !packed) return fail(GSL_EINVAL, "gsl_tile_codes: null pointer");
     if ((uintptr_t)packed & 15) return fail(GSL_EINVAL, "gsl_tile_codes: packed must be 16-byte aligned");
     if (packed_map_bytes(seg_w, seg_h) > 0x7fffffffLL) return fail(GSL_EINVAL, "gsl_tile_codes: map of %d x %d exceeds 2^31 packed bytes", seg_w, seg_h);
-    const uint32_t tx = map_tiles_x(seg_w), ty = map_tiles_y(seg_h);
-    const int64_t rows = (int64_t)tx * ty * 8 * n_maps;
-    int64_t blocks = (rows + 255) / 256;
+    const uint32_t sx = map_strips_x(seg_w), rp = map_rows_pad(seg_h);
+    const int64_t total = (int64_t)((sx + 3) / 4) * (rp / 8) * 32 * n_maps;
+    int64_t blocks = (total + 255) / 256;
     const int64_t cap = (int64_t)sm_count() * 16;
     if (blocks > cap) blocks = cap;
     const int vec_ok = ((uintptr_t)codes & 15) == 0 && (seg_w & 15) == 0;      // every 16-pixel run starts 16-byte aligned
-    tile_codes_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(codes, packed, n_maps, seg_w, seg_h, tx, ty, vec_ok);
+    tile_codes_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(codes, packed, n_maps, seg_w, seg_h, sx, rp, total, vec_ok);
     GSL_LAUNCH_CHECK("tile_codes_kernel");
     return GSL_OK;
 }

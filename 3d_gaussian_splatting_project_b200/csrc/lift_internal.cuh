@@ -1,4 +1,4 @@
-// Declarations shared by lift.cu, lift_order.cu and lift_sort.cu.
+// Declarations shared by lift.cu, lift_order.cu, lift_sort.cu and host_stage.cu.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -7,86 +7,81 @@
 
 namespace gsl {
 
-constexpr int kSheetTile = 256;        // Gaussians per vote-sheet tile == gather block size
+constexpr int kLiftThreads = 64;       // threads of a sweep CTA
+constexpr int kLiftPer = 2;            // Gaussians per thread (one packed float32x2 pair)
+constexpr int kTile = kLiftThreads * kLiftPer;    // Gaussians per tile == per sweep CTA
+constexpr int kWin = 16;               // views per window (staging unit of the view table)
 
 // ---------------------------------------------------------------------------------------
-// Packed label maps are TILED: a map of seg_w x seg_h codes is stored as 16 x 8-pixel tiles of
-// 128 bytes (one L1 line each; row r of a tile = 16 consecutive bytes), tile rows of
-// tiles_x = ceil(seg_w / 16) + 2 tiles, tiles_y = ceil(seg_h / 8) + 2 tile rows.  The extra
-// ring of tiles and the padding up to the tile multiple hold code 0 ("no vote"), so a pixel
-// up to 16 columns / 8 rows outside the map can be fetched like any other and votes for
-// nothing.  The lanes of a warp (spatially sorted Gaussians) project into a small 2-D patch;
-// tiling turns that patch into a handful of lines instead of one line per image row.
+// Packed label maps are stored in STRIPS: a map of seg_w x seg_h codes is cut into vertical
+// strips 16 pixels wide; inside a strip the rows follow each other, 16 bytes each.  There are
+// strips_x = ceil(seg_w / 16) + 2 strips of rows_pad = 8 * (ceil(seg_h / 8) + 2) rows: one ring
+// strip on the left, at least one on the right, 8 ring rows above and at least 8 below, all
+// holding code 0 ("no vote"), so a pixel up to 16 columns / 8 rows outside the map is fetched
+// like any other and votes for nothing.  Byte offset of pixel (x, y), with X = x + 16, Y = y + 8:
+//     off = (X >> 4) * (16 * rows_pad) + 16 * Y + (X & 15) = X + 16 Y + (X >> 4) * (16 rows_pad - 16)
+// A 128-byte line is a 16 x 8-pixel block (8 aligned rows of one strip): the lanes of a warp
+// (spatially sorted Gaussians) project into a small 2-D patch, which this layout turns into a
+// handful of lines instead of one line per image row, and the offset is three integer
+// operations on values the float32 screening has in registers anyway (lift.cu).
 // ---------------------------------------------------------------------------------------
-__host__ __device__ inline uint32_t map_tiles_x(int seg_w) { return (uint32_t)((seg_w + 15) >> 4) + 2u; }
-__host__ __device__ inline uint32_t map_tiles_y(int seg_h) { return (uint32_t)((seg_h + 7) >> 3) + 2u; }
+__host__ __device__ inline uint32_t map_strips_x(int seg_w) { return (uint32_t)((seg_w + 15) >> 4) + 2u; }
+__host__ __device__ inline uint32_t map_rows_pad(int seg_h) { return ((uint32_t)((seg_h + 7) >> 3) + 2u) * 8u; }
 inline int64_t packed_map_bytes(int seg_w, int seg_h)
 {
-    return (int64_t)map_tiles_x(seg_w) * (int64_t)map_tiles_y(seg_h) * 128;
+    return (int64_t)map_strips_x(seg_w) * (int64_t)map_rows_pad(seg_h) * 16;
 }
-// byte offset of pixel (xs, ys), xs in [-16, seg_w + 15], ys in [-8, seg_h + 7]; pitch = tiles_x * 128
-__device__ __forceinline__ uint32_t tiled_offset(uint32_t pitch, int xs, int ys)
+// byte offset of pixel (xs, ys), xs in [-16, seg_w + 15], ys in [-8, seg_h + 7]; strip = 16 * rows_pad
+__device__ __forceinline__ uint32_t strip_offset(uint32_t strip, int xs, int ys)
 {
     const uint32_t xb = (uint32_t)(xs + 16), yb = (uint32_t)(ys + 8);
-    return (yb >> 3) * pitch + ((xb >> 4) << 7) + ((yb & 7u) << 4) + (xb & 15u);
+    return (xb >> 4) * strip + (yb << 4) + (xb & 15u);
 }
 
-// Device-side view, in two parts.  HotView is everything the float32 sweep reads per pair: 80
-// bytes, 16-byte aligned, the views of a window back to back, so a view arrives in five wide
-// uniform constant loads and the whole window is 1.3 KB of constant cache.
+// Everything the float32 sweep reads per (Gaussian, view) pair: 80 bytes, 16-byte aligned, the
+// views of a window back to back in shared memory (five broadcast LDS.128 per view).
 struct alignas(16) HotView {
-    // the camera rounded to float32, rows 0 and 1 pre-multiplied by fx, fy; half_w / half_h hold
-    // width/2 - 1/2, height/2 - 1/2 (lift.cu: screen_pair)
-    float R[9], t[3], half_w, half_h;
-    float x_hi, y_hi;       // width + 2, height + 2: clamp range of the screened coordinate
-    int64_t map_offset;     // byte offset of the view's packed map
-    uint32_t pitch_m128;    // pitch - 128 and the folded constant of the float-derived offset
-    uint32_t addr_k;        //   (lift.cu: screen_pair)
+    // the camera rounded to float32, rows 0 and 1 pre-multiplied by fx, fy
+    float R[9], t[3];
+    float hwp, hhp;         // width/2 - 1/2 + 16, height/2 - 1/2 + 8: image coordinate minus 1/2, in ring coordinates
+    uint32_t xmax_bits;     // float bits of width + 18 / height + 10: unsigned-min clamp of the ring coordinate
+    uint32_t ymax_bits;
+    uint32_t strip_m16;     // 16 * rows_pad - 16
+    uint32_t addr_k;        // folded constant of the float-derived offset (lift.cu: fast_pair), modulo 2^32
+    uint64_t map;           // byte offset of the view's packed map; the sweep's staged copy holds its address
 };
+static_assert(sizeof(HotView) == 80, "HotView is five 16-byte words");
 
-// ColdView: the public GslView (float64 path) plus facts the host derives once per view.
-struct ColdView {
-    GslView g;
-    uint32_t pitch;    // bytes per tile row of this view's packed map
-    int wi, hi;        // width, height as integers
-    int unit_scale;    // scale_x == 1 && scale_y == 1: the rescale of dls:281-282 is the identity
-    int no_clamp;      // unit scale and the map covers the camera frame: dls:285-286 cannot fire
-    int screen_ok;     // float32 screening applies: integer frame below 2^21 px, finite parameters
-    int border_ok;     // unit scale and the map IS the camera frame: pixels just outside the frame
-                       // land in the zero ring of the tiled map, no bounds test needed
+// What the other code paths need of a view (per-pair bound, rescaled maps, float64 evaluation):
+// the public GslView plus facts the host derives once.
+struct ViewFacts {
+    float g_rm, g_tm;       // ec = g_rm * (|X|+|Y|+|Z|) + g_tm bounds the error of a camera coordinate
+    float fxh;              // >= max(5, |fx| + width/2, |fy| + height/2) (1 + 2e-6)
+    float c0;               // 2.01 u max(half_w, half_h) + 1e-6 (+ ring shift)
+    float span;             // max(width, height) + 18: largest |ring coordinate| after the clamp
+    int wi, hi;             // width, height as integers (0 when the frame is not integral)
+    int flags;              // kViewScreen | kViewBorder
+    uint32_t strip;         // 16 * rows_pad of the view's packed map
+    uint32_t pad_;
 };
+constexpr int kViewScreen = 1;    // float32 screening applies: integer frame below 2^21 px, finite parameters
+constexpr int kViewBorder = 2;    // unit scale and the map IS the camera frame: out-of-frame pixels read the zero ring
 
-// A window of views as the float64 kernel (lift_gather_kernel) takes it: by value, as a kernel
-// parameter (constant bank 0, compile-time offsets).
-template <int VW>
-struct ViewWindow {
-    ColdView c[VW];
-};
-
-// One window of the float32 sweep as it lies in device memory (workspace): a single launch covers
-// many windows, block (tile, window) reads its window's entry.  gsl_lift_prepare uploads the table
-// of all 16-view windows once (entries [0, ceil(V / 16))), before any label map is in flight, so
-// the sweeps need no host-to-device copy of their own (it would queue behind the map uploads of a
-// pipelined caller); 8-view windows (view_window <= 8) are built per call behind that table.
-struct alignas(16) WinDev {
-    HotView h[16];
-    // constants of the screening bounds, valid for all views of the window (lift.cu: screen_pair):
-    // ec = g_rm * (|X|+|Y|+|Z|) + g_tm  (camera coordinate) and
-    // 1/2 - E = k * fxh_neg + room0 - (k + 3.04 u) |x|,  k = ec / cz  (image coordinate)
-    float g_rm, g_tm, fxh_neg, room0;
-    int n_live;        // views of the window (<= 16)
-    int border;        // every view has border_ok
-    int word0;         // first sheet word of the window = first_view / 4
-    int first_view;
-};
+// Per (tile, view) verdict of the culling pass, 16 bits:
+//   0        no Gaussian of the tile can be visible in the view: skipped
+//   1..65533 fast path: every Gaussian of the tile is in front of the camera and the float32 error
+//            of an image coordinate is below E for all of them; value = floor((1/2 - E) * 2^17)
+//   65534    exact path: float64 expressions for every pair (views the screening does not cover)
+//   65535    general path: float32 screening with a per-pair bound
+constexpr unsigned kVerdictCull = 0u, kVerdictF64 = 65534u, kVerdictGeneral = 65535u;
 
 // Byte offsets of the pieces of the lifting workspace (each 256-byte aligned).
 struct OrderWs {
-    size_t sheet, pos_sorted, perm, keys, keys_sorted, idx, sort_temp, sort_temp_bytes, stats, tilebox, masks, views, planes, wins, bytes;
+    size_t pos_sorted, perm, keys, keys_sorted, idx, sort_temp, sort_temp_bytes, stats, tilebox, verdict, views, facts, hot, planes, bytes;
 };
 
 OrderWs order_layout(int64_t N, int V);
-int order_gaussians(const float *pos, int64_t N, int V, unsigned char *base, const OrderWs &L, cudaStream_t st);
+int order_gaussians(const float *pos, int64_t N, int V, bool sort, bool exact_only, unsigned char *base, const OrderWs &L, cudaStream_t st);
 
 // lift_sort.cu: stable radix sort of (24-bit cell key, row index) pairs.
 size_t sort_temp_capacity(int64_t N);

@@ -1,16 +1,16 @@
-// Spatial ordering and per-tile frustum culling for the lifting kernels, sm_100a.
+// Spatial ordering and the per-(tile, view) verdicts of the lifting sweep, sm_100a.
 //
 // The vote of a Gaussian depends only on its own position, so the order in which Gaussians are
 // processed is free.  Processing them in Morton order makes (i) the 32 Gaussians of a warp
 // project into a small 2-D patch of every view, so that a gather request touches a few lines
-// of the tiled label map instead of 32, and (ii) every 256-Gaussian tile of the gather kernel a
-// small box in space, so that a whole (tile, view) can be proven invisible -- behind the camera
-// or outside the image for every point of the box -- with a few interval evaluations, and
-// skipped.  On the reference's own cameras (bundled cameras.json) only ~13 % of
-// (Gaussian, view) pairs are visible, so culling removes most of the work; on the synthetic
-// look-at scenes it removes the ~25 % that is invisible.  Labels are unaffected: the gather
-// kernel still evaluates the reference's exact test for every pair it does not skip, and the
-// cull is conservative (margins ten times its own float32 rounding error, never the other way).
+// of the packed label map instead of 32, (ii) every 128-Gaussian tile of the sweep a small box in
+// space, so that a whole (tile, view) can be proven invisible -- behind the camera or outside the
+// image for every point of the box -- and skipped, or proven to lie in front of the camera with a
+// float32 error bound that holds for the whole tile, which is what makes the sweep's fast path two
+// compares per pair, and (iii) the tiles resident on the GPU at a time neighbours in space, so the
+// parts of the label maps they touch stay in L2.  Labels are unaffected: the sweep still evaluates
+// the reference's exact test for every pair it does not skip, and every verdict is conservative
+// (margins ten times the float32 rounding error of its own evaluation, never the other way).
 //
 //   order_stats_kernel    min/max (ordered-uint atomics) and first two moments (float64
 //                         atomics, one per CTA) of the finite coordinates
@@ -19,9 +19,9 @@
 //                         code; non-finite positions take the last key
 //   sort_cells            (key, row) pairs by key (lift_sort.cu)
 //   order_permute_kernel  pos_sorted[i] = pos[perm[i]]
-//   order_tilebox_kernel  bounding box (+ non-finite flag) of each run of 256 sorted Gaussians
+//   order_tilebox_kernel  bounding box (+ non-finite flag) of each run of 128 sorted Gaussians
 //   order_planes_kernel   per view, the five half-spaces of the visibility test as linear forms
-//   order_cull_kernel     one bit per (tile, view), 16 views to a mask word, all views in one launch
+//   order_verdict_kernel  16 bits per (tile, view): cull / fast with its bound / general / exact
 // The order inside a cell follows the input order (the sort is stable), so the whole ordering is
 // deterministic.  (A 1024^3 grid with 30-bit keys was measured: one more sort pass, same gather time.)
 #include "common.cuh"
@@ -143,6 +143,13 @@ order_key_kernel(const float *__restrict__ pos, int64_t N, const unsigned long l
 }
 
 __global__ void __launch_bounds__(256)
+order_iota_kernel(int32_t *__restrict__ perm, int64_t N)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) perm[i] = (int32_t)i;
+}
+
+__global__ void __launch_bounds__(256)
 order_permute_kernel(const float *__restrict__ pos, int64_t N, const int32_t *__restrict__ perm, float *__restrict__ pos_sorted)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -153,7 +160,7 @@ order_permute_kernel(const float *__restrict__ pos, int64_t N, const int32_t *__
     pos_sorted[3 * i + 2] = pos[3 * s + 2];
 }
 
-// One warp per tile of kSheetTile sorted Gaussians: box[tile] = {lo xyz, hi xyz, nonfinite, 0}.
+// One warp per tile of kTile sorted Gaussians: box[tile] = {lo xyz, hi xyz, nonfinite, 0}.
 __global__ void __launch_bounds__(256)
 order_tilebox_kernel(const float *__restrict__ pos_sorted, int64_t N, int64_t n_tiles, float *__restrict__ box)
 {
@@ -162,8 +169,8 @@ order_tilebox_kernel(const float *__restrict__ pos_sorted, int64_t N, int64_t n_
     if (tile >= n_tiles) return;
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
     int bad = 0;
-    for (int r = lane; r < kSheetTile; r += 32) {
-        const int64_t g = tile * kSheetTile + r;
+    for (int r = lane; r < kTile; r += 32) {
+        const int64_t g = tile * kTile + r;
         if (g >= N) break;
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
@@ -231,11 +238,13 @@ __device__ __forceinline__ void lin_range(const float4 pl, const float (&lo)[3],
 // Can any point of the box pass the visibility test in this view?  Conservative: float32
 // evaluation (coefficients rounded once, four roundings per form: error < 1e-6 * mag) against
 // margins of 1e-5 * mag plus 1e-6 px, so "no" is only ever said with room to spare; NaN says yes.
-__device__ __forceinline__ bool box_may_be_visible(const float4 *__restrict__ pl, const float (&lo)[3], const float (&hi)[3])
+// cz_lo = a lower bound of cz over the box (same margin).
+__device__ __forceinline__ bool box_may_be_visible(const float4 *__restrict__ pl, const float (&lo)[3], const float (&hi)[3], float &cz_lo)
 {
     const float rel = 1e-5f, px = 1e-6f;
     float mn, mx, mag;
     lin_range(pl[0], lo, hi, mn, mx, mag);
+    cz_lo = mn - (rel * mag + 1e-30f);
     if (mx < -(rel * mag + 1e-30f)) return false;                          // every point has z <= 0
     const float zpos = fmaxf(mx, 0.f) * px;
     lin_range(pl[1], lo, hi, mn, mx, mag);
@@ -249,41 +258,57 @@ __device__ __forceinline__ bool box_may_be_visible(const float4 *__restrict__ pl
     return true;
 }
 
-// Thread per (tile, view); 16 consecutive lanes share a tile and fill one 16-bit mask word:
-// masks[tile * n_words16 + v / 16], bit v % 16.
+// Thread per (tile, view): the verdict the sweep acts on (lift_internal.cuh).  For the fast path
+// the error bound of lift.cu (screen_pair) is evaluated once for the whole tile: with
+// a >= |X|+|Y|+|Z| over the box and cz >= cz_lo > 0,
+//     k_max = (g_rm a + g_tm) / cz_lo,   E = k_max (FXH + span) + 3.03 u span + c0,
+// every factor rounded up; 1/2 - E, rounded down to a multiple of 2^-17, is what a pair's offset
+// from the pixel centre is compared with.
 __global__ void __launch_bounds__(256)
-order_cull_kernel(const float *__restrict__ box, int64_t n_tiles, const float4 *__restrict__ planes, int V,
-                  uint16_t *__restrict__ masks, int n_words16)
+order_verdict_kernel(const float *__restrict__ box, int64_t n_tiles, const float4 *__restrict__ planes,
+                     const ViewFacts *__restrict__ facts, int V, int v_pad, int cull, int exact_only,
+                     uint16_t *__restrict__ verdict)
 {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int vpad = n_words16 * 16;
-    const int64_t tile = idx / vpad;
-    const int v = (int)(idx - tile * vpad);
-    bool vis = false;
-    if (tile < n_tiles && v < V) {
+    const int64_t tile = idx / v_pad;
+    const int v = (int)(idx - tile * v_pad);
+    if (tile >= n_tiles) return;
+    unsigned out = kVerdictCull;
+    if (v < V) {
         const float *b = box + tile * 8;
-        if (b[6] != 0.f) {
-            vis = true;                                                     // non-finite member: never cull
-        } else {
+        const ViewFacts f = facts[v];
+        const unsigned slow = ((f.flags & kViewScreen) && !exact_only) ? kVerdictGeneral : kVerdictF64;
+        out = slow;
+        if (b[6] == 0.f) {                                                  // a non-finite member: never cull, never fast
             const float lo[3] = {b[0], b[1], b[2]}, hi[3] = {b[3], b[4], b[5]};
-            vis = box_may_be_visible(planes + (size_t)v * 5, lo, hi);
+            float cz_lo;
+            const bool vis = box_may_be_visible(planes + (size_t)v * 5, lo, hi, cz_lo);
+            if (!vis && cull) {
+                out = kVerdictCull;
+            } else if (slow == kVerdictGeneral && (f.flags & kViewBorder) && cz_lo > 0.f) {
+                const float a = (fmaxf(fabsf(lo[0]), fabsf(hi[0])) + fmaxf(fabsf(lo[1]), fabsf(hi[1])) + fmaxf(fabsf(lo[2]), fabsf(hi[2]))) * 1.000002f;
+                const float ec = (f.g_rm * a + f.g_tm) * 1.000001f;
+                const float k = (ec / cz_lo) * 1.000002f;                   // covers r <= (1 / cz)(1 + 2.1 u)
+                const float E = (k * (f.fxh + f.span) * 1.000002f + 1.8119812e-07f * f.span + f.c0) * 1.000001f;
+                const float room = 0.5f - E;                                // exact or rounded to nearest: inside c0's 1e-6
+                if (room >= 0.25f && a < 1e15f) {                           // false for NaN
+                    unsigned q = (unsigned)(room * 131072.f) - 1u;          // floor, minus one step for the rounding of `room`
+                    out = q > 65533u ? 65533u : q;
+                }
+            }
         }
     }
-    const unsigned bal = __ballot_sync(0xffffffffu, vis);
-    const int lane = threadIdx.x & 31;
-    if (tile < n_tiles && (lane & 15) == 0)
-        masks[tile * n_words16 + (v >> 4)] = (uint16_t)((bal >> (lane & 16)) & 0xffffu);
+    verdict[tile * v_pad + v] = (uint16_t)out;
 }
 
 OrderWs order_layout(int64_t N, int V)
 {
     OrderWs o;
-    const int64_t n_pad = (N + kSheetTile - 1) / kSheetTile * kSheetTile;
-    const int64_t n_tiles = n_pad / kSheetTile;
-    const int64_t n_words16 = (V + 15) / 16;
+    const int64_t n_pad = (N + kTile - 1) / kTile * kTile;
+    const int64_t n_tiles = n_pad / kTile;
+    const int64_t v_pad = (V + kWin - 1) / kWin * kWin;
     size_t off = 0;
     auto take = [&](size_t bytes) { const size_t at = off; off += align_up(bytes, 256); return at; };
-    o.sheet = take((size_t)((V + 3) / 4) * (size_t)n_pad * sizeof(uint32_t));
     o.pos_sorted = take((size_t)n_pad * 3 * sizeof(float));
     o.perm = take((size_t)n_pad * sizeof(int32_t));
     o.keys = take((size_t)n_pad * sizeof(uint32_t));
@@ -293,17 +318,19 @@ OrderWs order_layout(int64_t N, int V)
     o.sort_temp = take(o.sort_temp_bytes);
     o.stats = take(kStatsBytes);
     o.tilebox = take((size_t)n_tiles * 8 * sizeof(float));
-    o.masks = take((size_t)n_tiles * (size_t)n_words16 * sizeof(uint16_t));
+    o.verdict = take((size_t)n_tiles * (size_t)(v_pad > 0 ? v_pad : kWin) * sizeof(uint16_t));
     o.views = take((size_t)(V > 0 ? V : 1) * sizeof(GslView));
+    o.facts = take((size_t)(V > 0 ? V : 1) * sizeof(ViewFacts));
+    o.hot = take((size_t)(v_pad > 0 ? v_pad : kWin) * sizeof(HotView));
     o.planes = take((size_t)(V > 0 ? V : 1) * 5 * sizeof(float4));
-    o.wins = take((size_t)((V + 15) / 16 + (V + 7) / 8 + 1) * sizeof(WinDev));
     o.bytes = off + 256;
     return o;
 }
 
-// Sort positions into Morton order, box the tiles, and decide per (tile, view) whether the view
-// must be swept.  All launches on `st`; the view table is already in the workspace (gsl_lift_prepare).
-int order_gaussians(const float *pos, int64_t N, int V, unsigned char *base, const OrderWs &L, cudaStream_t st)
+// Sort positions into Morton order (sort = false: keep the caller's order), box the tiles, and
+// decide per (tile, view) how the sweep treats it.  All launches on `st`; the view tables are
+// already in the workspace (gsl_lift_prepare).
+int order_gaussians(const float *pos, int64_t N, int V, bool sort, bool exact_only, unsigned char *base, const OrderWs &L, cudaStream_t st)
 {
     float *pos_sorted = reinterpret_cast<float *>(base + L.pos_sorted);
     int32_t *perm = reinterpret_cast<int32_t *>(base + L.perm);
@@ -312,34 +339,40 @@ int order_gaussians(const float *pos, int64_t N, int V, unsigned char *base, con
     int32_t *idx = reinterpret_cast<int32_t *>(base + L.idx);
     unsigned long long *stats = reinterpret_cast<unsigned long long *>(base + L.stats);
     float *tilebox = reinterpret_cast<float *>(base + L.tilebox);
-    uint16_t *masks = reinterpret_cast<uint16_t *>(base + L.masks);
+    uint16_t *verdict = reinterpret_cast<uint16_t *>(base + L.verdict);
     GslView *d_views = reinterpret_cast<GslView *>(base + L.views);
+    const ViewFacts *d_facts = reinterpret_cast<const ViewFacts *>(base + L.facts);
     float4 *planes = reinterpret_cast<float4 *>(base + L.planes);
-    const int64_t n_tiles = (N + kSheetTile - 1) / kSheetTile;
-    const int n_words16 = (V + 15) / 16;
+    const int64_t n_tiles = (N + kTile - 1) / kTile;
+    const int v_pad = (V + kWin - 1) / kWin * kWin;
 
-    GSL_CUDA_TRY(cudaMemsetAsync(stats, 0xff, 3 * 8, st));
-    GSL_CUDA_TRY(cudaMemsetAsync(stats + 3, 0x00, kStatsBytes - 3 * 8, st));
-    int64_t blocks = (N + 256 * 8 - 1) / (256 * 8);
-    const int64_t cap = (int64_t)sm_count() * 8;
-    if (blocks > cap) blocks = cap;
-    order_stats_kernel<<<(unsigned)blocks, 256, 0, st>>>(pos, N, stats);
-    GSL_LAUNCH_CHECK("order_stats_kernel");
-    order_grid_kernel<<<1, 32, 0, st>>>(stats);
-    GSL_LAUNCH_CHECK("order_grid_kernel");
     const unsigned rows_grid = (unsigned)((N + 255) / 256);
-    order_key_kernel<<<rows_grid, 256, 0, st>>>(pos, N, stats, keys, idx);
-    GSL_LAUNCH_CHECK("order_key_kernel");
-    if (int rc = sort_cells(keys, keys_sorted, idx, perm, N, base + L.sort_temp, L.sort_temp_bytes, st)) return rc;
+    if (sort) {
+        GSL_CUDA_TRY(cudaMemsetAsync(stats, 0xff, 3 * 8, st));
+        GSL_CUDA_TRY(cudaMemsetAsync(stats + 3, 0x00, kStatsBytes - 3 * 8, st));
+        int64_t blocks = (N + 256 * 8 - 1) / (256 * 8);
+        const int64_t cap = (int64_t)sm_count() * 8;
+        if (blocks > cap) blocks = cap;
+        order_stats_kernel<<<(unsigned)blocks, 256, 0, st>>>(pos, N, stats);
+        GSL_LAUNCH_CHECK("order_stats_kernel");
+        order_grid_kernel<<<1, 32, 0, st>>>(stats);
+        GSL_LAUNCH_CHECK("order_grid_kernel");
+        order_key_kernel<<<rows_grid, 256, 0, st>>>(pos, N, stats, keys, idx);
+        GSL_LAUNCH_CHECK("order_key_kernel");
+        if (int rc = sort_cells(keys, keys_sorted, idx, perm, N, base + L.sort_temp, L.sort_temp_bytes, st)) return rc;
+    } else {
+        order_iota_kernel<<<rows_grid, 256, 0, st>>>(perm, N);
+        GSL_LAUNCH_CHECK("order_iota_kernel");
+    }
     order_permute_kernel<<<rows_grid, 256, 0, st>>>(pos, N, perm, pos_sorted);
     GSL_LAUNCH_CHECK("order_permute_kernel");
     order_tilebox_kernel<<<(unsigned)((n_tiles + 7) / 8), 256, 0, st>>>(pos_sorted, N, n_tiles, tilebox);
     GSL_LAUNCH_CHECK("order_tilebox_kernel");
     order_planes_kernel<<<(V + 127) / 128, 128, 0, st>>>(d_views, V, planes);
     GSL_LAUNCH_CHECK("order_planes_kernel");
-    const int64_t threads = n_tiles * (int64_t)n_words16 * 16;
-    order_cull_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(tilebox, n_tiles, planes, V, masks, n_words16);
-    GSL_LAUNCH_CHECK("order_cull_kernel");
+    const int64_t threads = n_tiles * (int64_t)v_pad;
+    order_verdict_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(tilebox, n_tiles, planes, d_facts, V, v_pad, sort ? 1 : 0, exact_only ? 1 : 0, verdict);
+    GSL_LAUNCH_CHECK("order_verdict_kernel");
     return GSL_OK;
 }
 

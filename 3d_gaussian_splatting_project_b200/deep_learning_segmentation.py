@@ -13,8 +13,9 @@ The 2-D segmentation stage itself (SegFormer / Mask2Former / YOLO inference, ref
 :85-238) is upstream of this path and is not re-implemented.  `assign_labels` finds a
 segmenter in this order:
   1. the `segmenter=` argument: callable(image_path, output_dir, model_type) -> int array [H, W]
-  2. a precomputed `<output_dir>/<img_name>_segmap.npy`, the file the reference's
-     `segment_image` writes for every view (:165)
+  2. with GSLIFT_REUSE_SEGMAPS=1 only: a precomputed `<output_dir>/<img_name>_segmap.npy`, the
+     file the reference's `segment_image` writes for every view (:165); the reference itself
+     always recomputes, so reuse is opt-in and announced per view
   3. the reference's own `initialize_model` / `segment_image`, imported from the checkout
      named by $GSLIFT_REFERENCE_DIR
 """
@@ -107,68 +108,43 @@ class _UpstreamSegmenter:
 
 
 def _precomputed_map(output_dir, img_name):
+    """<output_dir>/<img_name>_segmap.npy, the file the reference's segment_image writes (:165).
+    The reference recomputes (and overwrites) it on every run; reusing it is therefore opt-in:
+    GSLIFT_REUSE_SEGMAPS=1, announced per view."""
+    if os.environ.get("GSLIFT_REUSE_SEGMAPS") != "1":
+        return None
     path = os.path.join(output_dir, f"{img_name}_segmap.npy") if output_dir else None
-    return np.load(path) if path and os.path.exists(path) else None
+    if path and os.path.exists(path):
+        print(f"Using precomputed segmentation map {path}")
+        return np.load(path)
+    return None
 
 
 # ----------------------------------------------------------------------------------------
 # the hot path
 # ----------------------------------------------------------------------------------------
-def _stage_maps(seg_maps, shapes, device, label_min, n_classes):
-    """Host int maps -> packed uint8 codes on the device (N2 of SURVEY 8f: label-map staging).
-
-    One process: upload every map (int32), device min/max picks a tight code range, pack.
-    Under torch.distributed every rank holds the same host maps but uploads and packs only its
-    contiguous block of views; the packed blocks (1 byte per pixel) are then broadcast rank by
-    rank over NCCL, so the PCIe cost per rank drops by the world size."""
-    import torch.distributed as dist
-    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-    rank = dist.get_rank() if world > 1 else 0
-    sizes = [h * w for h, w in shapes]
-    starts = np.concatenate(([0], np.cumsum(sizes))).astype(np.int64)     # pixels, row-major staging
-    pstarts = ops.packed_offsets(shapes)                                   # bytes, packed layout
-    total = int(pstarts[-1])
-    V = len(seg_maps)
-    per, extra = divmod(V, world)
-    cuts = [r * per + min(r, extra) for r in range(world + 1)]
-    v_lo, v_hi = cuts[rank], cuts[rank + 1]
-    mine = int(starts[v_hi] - starts[v_lo])
-    staged = torch.empty(mine, dtype=torch.int32, device=device)
-    off = 0
-    for v in range(v_lo, v_hi):
-        m = seg_maps[v]
-        src = m if isinstance(m, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(m, np.int32))
-        staged[off:off + sizes[v]].copy_(src.reshape(-1), non_blocking=True)
-        off += sizes[v]
-    if label_min is None or n_classes is None:
-        # tight code range from the data (device min/max): fewer histogram rows per Gaussian
-        lo, hi = ops.label_range(staged) if mine else (2**31 - 1, -2**31)
-        if world > 1:
-            mm = torch.tensor([lo, -hi], dtype=torch.int64, device=device)
-            dist.all_reduce(mm, op=dist.ReduceOp.MIN)
-            lo, hi = int(mm[0].item()), -int(mm[1].item())
-        if int(starts[-1]) == 0:
-            lo, hi = ops.DEFAULT_LABEL_MIN, ops.DEFAULT_LABEL_MIN
-        if hi - lo + 1 > ops.DEFAULT_N_CLASSES:
-            raise ValueError(f"label maps span {hi - lo + 1} values; at most {ops.DEFAULT_N_CLASSES} are supported")
-        label_min, n_classes = lo, hi - lo + 1
-    packed = torch.empty(total, dtype=torch.uint8, device=device)
-    if mine:
-        ops.pack_labels(staged, shapes[v_lo:v_hi], label_min, n_classes, out=packed[int(pstarts[v_lo]):int(pstarts[v_hi])])
-    if world > 1:
-        for r in range(world):
-            lo_px, hi_px = int(pstarts[cuts[r]]), int(pstarts[cuts[r + 1]])
-            if hi_px > lo_px:
-                dist.broadcast(packed[lo_px:hi_px], src=r)
-    return packed, label_min, n_classes
-
-
 _copy_streams = {}
 last_call_stats = {}               # bytes lift_labels moved over PCIe in its last call (this process)
-_pinned_codes = {}                 # pinned uint8 staging for host-narrowed views, by size
+_pinned_codes = {}                 # pinned uint8 staging for host-narrowed views (grown to the largest scene seen)
 _host_stage = {"px_per_s": None, "fixed_s": 0.008}   # calibrated by use: host narrowing rate (pixels per second, all
                                                       # threads, with the DMA engine running) and the other host time of a call
 _PCIE_BYTES_PER_S = 54e9           # pinned host -> device copy rate of a PCIe 5 x16 link (profiles/probes/h2d_probe.py)
+_symm_packed = {}                  # per (device, bytes): symmetric-memory packed buffer of the multi-rank staging
+CH = 16                            # views per staging chunk
+
+
+def _dist():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist, dist.get_world_size(), dist.get_rank()
+    return None, 1, 0
+
+
+def _copy_stream(device):
+    key = (device.type, device.index)
+    if key not in _copy_streams:
+        _copy_streams[key] = torch.cuda.Stream(device)
+    return _copy_streams[key]
 
 
 def _host_cores():
@@ -210,22 +186,70 @@ def _host_ptr(m):
     return arr.ctypes.data, arr
 
 
-def _lift_pipelined(positions, cameras, image_sizes, seg_maps, shapes, device):
-    """One-process fast path of lift_labels from HOST maps, organised around the PCIe transfer,
-    which is what such a call waits for:
+def _as_int32_tensor(m):
+    return m if isinstance(m, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(m, np.int32))
 
-      * the first windows of 16 views cross the bus as int32, two staging buffers in flight on a
+
+def _copy_views(seg_maps, sizes, v0, v1, dst):
+    """Enqueue (current stream) the copies of maps [v0, v1) into the flat int32 device tensor `dst`;
+    maps that lie back to back in one host allocation (slices of one big pinned tensor) cross in a
+    single copy.  Returns the number of pixels."""
+    off, v = 0, v0
+    while v < v1:
+        src = _as_int32_tensor(seg_maps[v])
+        n, last = sizes[v], v
+        if src.dtype == torch.int32 and src.is_contiguous() and not src.is_cuda:
+            while last + 1 < v1:
+                nxt = seg_maps[last + 1]
+                if not (isinstance(nxt, torch.Tensor) and nxt.dtype == torch.int32 and nxt.is_contiguous() and not nxt.is_cuda
+                        and nxt.untyped_storage().data_ptr() == src.untyped_storage().data_ptr()
+                        and nxt.storage_offset() == src.storage_offset() + n):
+                    break
+                last += 1
+                n += sizes[last]
+            flat = torch.as_strided(src, (n,), (1,), src.storage_offset())
+        else:
+            flat = src.reshape(-1)
+        dst[off:off + n].copy_(flat, non_blocking=True)
+        off += n
+        v = last + 1
+    return off
+
+
+def _runs(shapes, v0, v1):
+    """(first view, count) of the runs of equal map shapes among views [v0, v1)."""
+    v = v0
+    while v < v1:
+        n = 1
+        while v + n < v1 and shapes[v + n] == shapes[v]:
+            n += 1
+        yield v, n
+        v += n
+
+
+class _Staged:
+    """Packed maps on the device plus the code window they were packed with."""
+
+    def __init__(self, packed, label_min, n_classes, lo, hi, h2d_bytes, views_as_int32, views_narrowed):
+        self.packed, self.label_min, self.n_classes = packed, label_min, n_classes
+        self.lo, self.hi = lo, hi                      # value range seen in the maps
+        self.h2d_bytes, self.views_as_int32, self.views_narrowed = h2d_bytes, views_as_int32, views_narrowed
+
+
+def _stage_pipelined(seg_maps, shapes, device, before_wait=None):
+    """One-process staging of HOST (or device) maps, organised around the PCIe transfer, which is
+    what such a call waits for (N2 of SURVEY 8f):
+
+      * the first chunks of 16 views cross the bus as int32, two staging buffers in flight on a
         copy stream, and are packed on the device (gsl_pack_labels);
-      * the remaining windows are narrowed to 1-byte codes by the host cores meanwhile
-        (gsl_host_pack_labels), cross as uint8 behind the int32 windows, and are tiled on the
-        device (gsl_tile_codes);
-      * every window is swept as soon as its packed maps are resident (gsl_lift_prepare once, then
-        gsl_lift_gather_range per window / batch), so only the last sweep and the majority are not
-        hidden behind the transfer.
+      * the remaining chunks are narrowed to 1-byte codes by the host cores meanwhile
+        (gsl_host_pack_labels), cross as uint8 behind the int32 chunks, and are laid out on the
+        device (gsl_tile_codes).
 
-    The first uploads are enqueued before anything else happens on the host.  Codes are label + 2
-    (label_min = -1); returns None when the labels do not fit that window and the caller must take
-    the general path."""
+    The first uploads are enqueued before anything else happens on the host; `before_wait` (the
+    Gaussian ordering, which reads no maps) is called right after them.  Codes are label + 2
+    (label_min = -1, 255 codes); the caller checks the value range and re-stages when the labels do
+    not fit that window."""
     import ctypes
     import time
     from ._native import check, lib
@@ -235,113 +259,72 @@ def _lift_pipelined(positions, cameras, image_sizes, seg_maps, shapes, device):
     starts = np.concatenate(([0], np.cumsum(sizes))).astype(np.int64)     # pixels, row-major staging
     pstarts = ops.packed_offsets(shapes)                                   # bytes, packed layout
     main = torch.cuda.current_stream(device)
-    key = (device.type, device.index)
-    if key not in _copy_streams:
-        _copy_streams[key] = torch.cuda.Stream(device)
-    copy = _copy_streams[key]
-    CH = 16
+    copy = _copy_stream(device)
+    copy.wait_stream(main)          # device-resident maps may still be being written; freed blocks may still be in use
     chunks = list(range(0, V, CH))
     n_host = int(round(_host_fraction(seg_maps, int(starts[-1])) * len(chunks)))
-    n_dev = len(chunks) - n_host                                 # windows [0, n_dev) cross as int32
+    n_dev = len(chunks) - n_host                                 # chunks [0, n_dev) cross as int32
     chunk_px = max([int(starts[min(v0 + CH, V)] - starts[v0]) for v0 in chunks[:n_dev]] + [1])
-    slots = [torch.empty(chunk_px, dtype=torch.int32, device=device) for _ in range(2)]
+    with torch.cuda.stream(copy):
+        slots = [torch.empty(chunk_px, dtype=torch.int32, device=device) for _ in range(2)]
+    for sl in slots:
+        sl.record_stream(main)
     slot_free = [None, None]
     ready = [None] * n_dev
 
     def upload(ci):
         v0 = chunks[ci]
-        v1 = min(v0 + CH, V)
-        buf = slots[ci % 2]
         with torch.cuda.stream(copy):
             if slot_free[ci % 2] is not None:
                 copy.wait_event(slot_free[ci % 2])
-            off, v = 0, v0
-            while v < v1:
-                m = seg_maps[v]
-                src = m if isinstance(m, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(m, np.int32))
-                n, last = sizes[v], v
-                # maps that lie back to back in one host allocation (slices of one big pinned tensor)
-                # cross in a single copy
-                if src.dtype == torch.int32 and src.is_contiguous() and not src.is_cuda:
-                    while last + 1 < v1:
-                        nxt = seg_maps[last + 1]
-                        if not (isinstance(nxt, torch.Tensor) and nxt.dtype == torch.int32 and nxt.is_contiguous() and not nxt.is_cuda
-                                and nxt.untyped_storage().data_ptr() == src.untyped_storage().data_ptr()
-                                and nxt.storage_offset() == src.storage_offset() + n):
-                            break
-                        last += 1
-                        n += sizes[last]
-                    flat = torch.as_strided(src, (n,), (1,), src.storage_offset())
-                else:
-                    flat = src.reshape(-1)
-                buf[off:off + n].copy_(flat, non_blocking=True)
-                off += n
-                v = last + 1
+            n = _copy_views(seg_maps, sizes, v0, min(v0 + CH, V), slots[ci % 2])
             ready[ci] = torch.cuda.Event()
             ready[ci].record(copy)
-        return off
+        return n
 
-    def pack_runs(fn, src_ptr, elem, v0, v1):
-        """fn = gsl_pack_labels / gsl_tile_codes over the runs of equal shapes of views [v0, v1)."""
-        v = v0
-        while v < v1:
-            n = 1
-            while v + n < v1 and shapes[v + n] == shapes[v]:
-                n += 1
-            yield fn, src_ptr + elem * int(starts[v] - starts[v0]), n, shapes[v][1], shapes[v][0], int(pstarts[v])
-            v += n
-
-    trace = os.environ.get("GSLIFT_TRACE") == "1"               # phase timings of this call on stderr
     t_call0 = time.perf_counter()
     with torch.cuda.device(device):
-        if trace:
-            import sys
-            t_host0 = time.perf_counter()
-            print(f"[gslift trace] pipeline starts at {t_host0:.6f}; {n_dev} windows as int32, {n_host} narrowed on the host", file=sys.stderr)
-            ev0 = torch.cuda.Event(enable_timing=True); ev0.record(main)
         n_px = [0] * n_dev
         for ci in range(min(2, n_dev)):                          # the transfer starts now
             n_px[ci] = upload(ci)
-        pos = positions if isinstance(positions, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(positions, np.float32))
-        pos = pos.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
-        views = ops.make_views(cameras, shapes, image_sizes)
-        N = pos.shape[0]
+        if before_wait is not None:
+            before_wait()
         packed = torch.empty(int(pstarts[-1]), dtype=torch.uint8, device=device)
-        ws = ops._ws.get(device, L.gsl_lift_workspace_bytes(N, V))
         minmax = torch.tensor([2**31 - 1, -2**31], dtype=torch.int32, device=device)
         err = torch.zeros(1, dtype=torch.int32, device=device)
-        vptr = views.ctypes.data
-        check(L.gsl_lift_prepare(pos.data_ptr(), N, vptr, V, ws.data_ptr(), ws.numel(), main.cuda_stream))
-        # ---- windows that cross as int32: everything below is enqueued without waiting
+        # ---- chunks that cross as int32: everything below is enqueued without waiting
         for ci in range(n_dev):
             v0 = chunks[ci]
             v1 = min(v0 + CH, V)
             buf = slots[ci % 2]
             main.wait_event(ready[ci])
             check(L.gsl_label_range(buf.data_ptr(), n_px[ci], minmax.data_ptr(), main.cuda_stream))
-            for _, src, n, w, h, dst in pack_runs(None, buf.data_ptr(), 4, v0, v1):
-                check(L.gsl_pack_labels(src, n, w, h, packed.data_ptr() + dst, -1, 255, err.data_ptr(), main.cuda_stream))
+            for v, n in _runs(shapes, v0, v1):
+                check(L.gsl_pack_labels(buf.data_ptr() + 4 * int(starts[v] - starts[v0]), n, shapes[v][1], shapes[v][0],
+                                        packed.data_ptr() + int(pstarts[v]), -1, 255, err.data_ptr(), main.cuda_stream))
             slot_free[ci % 2] = torch.cuda.Event()
             slot_free[ci % 2].record(main)
             if ci + 2 < n_dev:
                 n_px[ci + 2] = upload(ci + 2)            # refills the slot just packed
-            check(L.gsl_lift_gather_range(pos.data_ptr(), N, vptr, V, v0, v1, packed.data_ptr(), None, 0.0, 0,
-                                          ws.data_ptr(), ws.numel(), main.cuda_stream))
-        # ---- windows narrowed on the host, a few at a time, while the DMA engine is busy with the above
+        # ---- chunks narrowed on the host, a few at a time, while the DMA engine is busy with the above
         host_mm = (ctypes.c_int * 2)(2**31 - 1, -2**31)
         if n_host:
             hv0 = chunks[n_dev]
             host_px = int(starts[V] - starts[hv0])
             if _pinned_codes.get("n", 0) < host_px:
+                # sized for every view of the scene, so that a later call whose calibrated split moves
+                # more views to the host does not pay a pinned allocation inside its timed region
                 t_alloc = time.perf_counter()
-                _pinned_codes["buf"] = torch.empty(host_px, dtype=torch.uint8, pin_memory=True)
-                _pinned_codes["n"] = host_px
+                _pinned_codes["buf"] = torch.empty(int(starts[V]), dtype=torch.uint8, pin_memory=True)
+                _pinned_codes["n"] = int(starts[V])
                 t_call0 += time.perf_counter() - t_alloc         # a one-time cost, not part of the calibration
             pinned = _pinned_codes["buf"]
-            codes = torch.empty(host_px, dtype=torch.uint8, device=device)
+            with torch.cuda.stream(copy):
+                codes = torch.empty(host_px, dtype=torch.uint8, device=device)
+            codes.record_stream(main)
             bad = ctypes.c_int(0)
-            # host batches of two windows; the last two windows go one at a time, so that little is
-            # left to upload and sweep once the host is done
+            # host batches of two chunks; the last two chunks go one at a time, so that little is
+            # left to upload once the host is done
             batches, b0 = [], n_dev
             while b0 < len(chunks):
                 nb = 2 if len(chunks) - b0 > 3 else 1
@@ -364,35 +347,140 @@ def _lift_pipelined(positions, cameras, image_sizes, seg_maps, shapes, device):
                     landed = torch.cuda.Event()
                     landed.record(copy)
                 main.wait_event(landed)
-                for _, src, n, w, h, dst in pack_runs(None, codes.data_ptr() + off0, 1, vb0, vb1):
-                    check(L.gsl_tile_codes(src, n, w, h, packed.data_ptr() + dst, main.cuda_stream))
-                check(L.gsl_lift_gather_range(pos.data_ptr(), N, vptr, V, vb0, vb1, packed.data_ptr(), None, 0.0, 0,
-                                              ws.data_ptr(), ws.numel(), main.cuda_stream))
+                for v, n in _runs(shapes, vb0, vb1):
+                    check(L.gsl_tile_codes(codes.data_ptr() + int(starts[v] - starts[hv0]), n, shapes[v][1], shapes[v][0],
+                                           packed.data_ptr() + int(pstarts[v]), main.cuda_stream))
             if t_narrow > 0:
                 _host_stage["px_per_s"] = px_narrow / t_narrow
                 # the other host work of this call; first calls also pay allocations, hence the cap
                 _host_stage["fixed_s"] = min(max(time.perf_counter() - t_call0 - t_narrow, 0.0), 0.015)
         dev_px = int(starts[chunks[n_dev]] if n_dev < len(chunks) else starts[V])
-        last_call_stats.update(h2d_bytes=4 * dev_px + int(starts[V] - dev_px) + int(pos.numel()) * 4, d2h_bytes=N * 4,
-                               views_as_int32=min(n_dev * CH, V), views_narrowed_on_host=V - min(n_dev * CH, V))
-        if trace:
-            t_host1 = time.perf_counter()
-            ev_up = torch.cuda.Event(enable_timing=True); ev_up.record(copy)
-            ev_sw = torch.cuda.Event(enable_timing=True); ev_sw.record(main)
         lo, hi = (int(x) for x in minmax.tolist())           # synchronises: every copy has been consumed
         lo, hi = min(lo, int(host_mm[0])), max(hi, int(host_mm[1]))
-        if lo < -1 or hi > 253:
-            return None
-        labels = torch.empty(N, dtype=torch.int32, device=device)
-        check(L.gsl_lift_majority(N, V, -1, max(hi + 2, 1), labels.data_ptr(), ws.data_ptr(), ws.numel(), main.cuda_stream))
-        if trace:
-            ev_mj = torch.cuda.Event(enable_timing=True); ev_mj.record(main)
-            ev_mj.synchronize()
-            rate = _host_stage["px_per_s"]
-            print(f"[gslift trace] majority done at {time.perf_counter():.6f} | host enqueue + narrowing {1e3 * (t_host1 - t_host0):.2f} ms"
-                  f" ({'%.1f' % (rate / 1e9) if rate else '-'} Gpx/s) | uploads done +{ev0.elapsed_time(ev_up):.2f} ms | "
-                  f"last sweep done +{ev0.elapsed_time(ev_sw):.2f} ms | majority done +{ev0.elapsed_time(ev_mj):.2f} ms", file=sys.stderr)
-    return labels
+    return _Staged(packed, -1, 255, lo, hi, 4 * dev_px + int(starts[V] - dev_px), min(n_dev * CH, V), V - min(n_dev * CH, V))
+
+
+def _stage_sharded(seg_maps, shapes, device, dist, world, rank, before_wait=None):
+    """Multi-rank staging: every rank holds the same host maps but uploads and packs only its
+    contiguous block of views, chunk by chunk (two int32 staging buffers in flight on a copy
+    stream), and PUSHES every packed chunk straight into all ranks' packed buffers over peer
+    memory (torch symmetric memory = CUDA peer mapping over NVLink) while the next chunk crosses
+    PCIe.  The PCIe cost per rank drops by the world size and no collective library call sits on
+    the data path; one barrier at the end publishes the buffers."""
+    from ._native import check, lib
+    L = lib()
+    V = len(seg_maps)
+    sizes = [h * w for h, w in shapes]
+    starts = np.concatenate(([0], np.cumsum(sizes))).astype(np.int64)
+    pstarts = ops.packed_offsets(shapes)
+    total = int(pstarts[-1])
+    per, extra = divmod(V, world)
+    cuts = [r * per + min(r, extra) for r in range(world + 1)]
+    v_lo, v_hi = cuts[rank], cuts[rank + 1]
+    main = torch.cuda.current_stream(device)
+    copy = _copy_stream(device)
+    copy.wait_stream(main)
+    peers = None
+    use_symm = os.environ.get("GSLIFT_STAGE_EXCHANGE", "symm") != "nccl"
+    if use_symm:
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            key = (device.index, total)
+            if key not in _symm_packed:
+                _symm_packed.clear()                 # one scene at a time: drop the previous mapping
+                buf = symm_mem.empty(max(total, 16), dtype=torch.uint8, device=device)
+                hdl = symm_mem.rendezvous(buf, dist.group.WORLD.group_name)
+                _symm_packed[key] = (buf, hdl, [hdl.get_buffer(r, (max(total, 16),), torch.uint8) for r in range(world)])
+            packed, hdl, peers = _symm_packed[key]
+        except Exception:                            # no peer access on this machine: NCCL broadcast below
+            peers = None
+    if peers is None:
+        packed = torch.empty(total, dtype=torch.uint8, device=device)
+    else:
+        # nobody may still be sweeping the previous call's maps when the pushes of this one arrive
+        dist.barrier()
+    chunks = list(range(v_lo, v_hi, CH))
+    chunk_px = max([int(starts[min(v0 + CH, v_hi)] - starts[v0]) for v0 in chunks] + [1])
+    with torch.cuda.stream(copy):
+        slots = [torch.empty(chunk_px, dtype=torch.int32, device=device) for _ in range(2)]
+    for sl in slots:
+        sl.record_stream(main)
+    slot_free, ready, n_px = [None, None], [None] * len(chunks), [0] * len(chunks)
+
+    def upload(ci):
+        v0 = chunks[ci]
+        with torch.cuda.stream(copy):
+            if slot_free[ci % 2] is not None:
+                copy.wait_event(slot_free[ci % 2])
+            n_px[ci] = _copy_views(seg_maps, sizes, v0, min(v0 + CH, v_hi), slots[ci % 2])
+            ready[ci] = torch.cuda.Event()
+            ready[ci].record(copy)
+
+    with torch.cuda.device(device):
+        for ci in range(min(2, len(chunks))):
+            upload(ci)
+        if before_wait is not None:
+            before_wait()
+        minmax = torch.tensor([2**31 - 1, -2**31], dtype=torch.int32, device=device)
+        err = torch.zeros(1, dtype=torch.int32, device=device)
+        push = _push_stream(device)
+        for ci, v0 in enumerate(chunks):
+            v1 = min(v0 + CH, v_hi)
+            buf = slots[ci % 2]
+            main.wait_event(ready[ci])
+            check(L.gsl_label_range(buf.data_ptr(), n_px[ci], minmax.data_ptr(), main.cuda_stream))
+            for v, n in _runs(shapes, v0, v1):
+                check(L.gsl_pack_labels(buf.data_ptr() + 4 * int(starts[v] - starts[v0]), n, shapes[v][1], shapes[v][0],
+                                        packed.data_ptr() + int(pstarts[v]), -1, 255, err.data_ptr(), main.cuda_stream))
+            slot_free[ci % 2] = torch.cuda.Event()
+            slot_free[ci % 2].record(main)
+            if ci + 2 < len(chunks):
+                upload(ci + 2)
+            if peers is not None:                    # push this chunk to every peer while the next one uploads
+                done = torch.cuda.Event()
+                done.record(main)
+                a, b = int(pstarts[v0]), int(pstarts[v1])
+                with torch.cuda.stream(push):
+                    push.wait_event(done)
+                    for k in range(1, world):
+                        r = (rank + k) % world
+                        peers[r][a:b].copy_(packed[a:b], non_blocking=True)
+        mm = torch.stack([minmax[0].to(torch.int64), -minmax[1].to(torch.int64)])
+        dist.all_reduce(mm, op=dist.ReduceOp.MIN)
+        if peers is not None:
+            main.wait_stream(push)
+            torch.cuda.current_stream(device).synchronize()
+            dist.barrier()                           # every rank's pushes have landed everywhere
+        else:
+            for r in range(world):
+                a, b = int(pstarts[cuts[r]]), int(pstarts[cuts[r + 1]])
+                if b > a:
+                    dist.broadcast(packed[a:b], src=r)
+        lo, hi = int(mm[0].item()), -int(mm[1].item())
+    return _Staged(packed, -1, 255, lo, hi, 4 * int(starts[v_hi] - starts[v_lo]), V, 0)
+
+
+_push_streams = {}
+
+
+def _push_stream(device):
+    key = (device.type, device.index)
+    if key not in _push_streams:
+        _push_streams[key] = torch.cuda.Stream(device)
+    return _push_streams[key]
+
+
+def _stage_wide(seg_maps, shapes, device):
+    """Label sets that do not fit one 255-code window (reference dls:288-295 accepts any int32
+    label): all maps go to the device as int32 and every value is replaced by its rank among the
+    distinct values (dense ids), which the caller then lifts in passes of 255 ids.  Returns
+    (dense int32 maps flat, sorted distinct values)."""
+    sizes = [h * w for h, w in shapes]
+    staged = torch.empty(int(sum(sizes)), dtype=torch.int32, device=device)
+    _copy_views(seg_maps, sizes, 0, len(seg_maps), staged)
+    uniq = torch.unique(staged)                                  # sorted
+    dense = torch.searchsorted(uniq, staged).to(torch.int32)
+    return dense, uniq
 
 
 def lift_labels(positions, cameras, seg_maps, image_sizes=None, device=None, want_near=False,
@@ -401,34 +489,108 @@ def lift_labels(positions, cameras, seg_maps, image_sizes=None, device=None, wan
 
     positions   float32 [N,3] array or tensor (under torch.distributed: THIS rank's Gaussians)
     cameras     camera dicts, in voting order
-    seg_maps    list of int arrays [seg_h, seg_w] (NumPy or tensors), one per camera
+    seg_maps    list of int arrays [seg_h, seg_w] (NumPy or tensors), one per camera; any int32
+                label values (more than 255 distinct values are lifted in several passes)
     image_sizes per camera (orig_w, orig_h); default = the map's own size (scale 1.0)
+    label_min, n_classes  optional explicit code window (values outside it raise)
     Returns int32 NumPy labels (and the near-boundary mask when want_near).
     """
+    from ._native import check, lib
     device = torch.device(device if device is not None else "cuda")
-    if os.environ.get("GSLIFT_TRACE") == "1":
+    trace = os.environ.get("GSLIFT_TRACE") == "1"
+    if trace:
         import sys, time
-        print(f"[gslift trace] lift_labels entered at {time.perf_counter():.6f}", file=sys.stderr)
-    shapes = [tuple(m.shape) for m in seg_maps]
-    n_pos = positions.shape[0]
-    import torch.distributed as dist
-    single = not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
-    if (single and not want_near and label_min is None and n_classes is None and len(cameras) and n_pos
-            and all(len(sh) == 2 for sh in shapes)):
-        fast = _lift_pipelined(positions, cameras, image_sizes, seg_maps, shapes, device)
-        if fast is not None:
-            return _to_host(fast)
-    pos = positions if isinstance(positions, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(positions, np.float32))
-    pos = pos.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
-    views = ops.make_views(cameras, shapes, image_sizes)
-    packed, label_min, n_classes = _stage_maps(seg_maps, shapes, device, label_min, n_classes)
-    world = dist.get_world_size() if not single else 1
-    last_call_stats.update(h2d_bytes=4 * sum(h * w for h, w in shapes) // world + int(pos.numel()) * 4, d2h_bytes=int(pos.shape[0]) * 4,
-                           views_as_int32=len(shapes), views_narrowed_on_host=0)
-    res = ops.lift_votes(pos, views, packed, label_min, n_classes, want_near=want_near, near_eps=near_eps)
+        t_enter = time.perf_counter()
+    shapes = [tuple(int(x) for x in m.shape) for m in seg_maps]
+    if any(len(sh) != 2 for sh in shapes):
+        raise ValueError("every segmentation map must be 2-D [seg_h, seg_w]")
+    dist, world, rank = _dist()
+    V = len(cameras)
+    if len(seg_maps) != V:
+        raise ValueError("one segmentation map per camera")
+    L = lib()
+    main = torch.cuda.current_stream(device)
+    state = {}
+
+    def prepare():
+        """Positions to the device, view table, ordering + verdicts: needs no maps, so it is
+        enqueued right behind the first uploads."""
+        pos = positions if isinstance(positions, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(positions, np.float32))
+        pos = pos.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+        views = ops.make_views(cameras, shapes, image_sizes)
+        N = pos.shape[0]
+        ws = ops._ws.get(device, L.gsl_lift_workspace_bytes(N, V))
+        with torch.cuda.device(device):
+            check(L.gsl_lift_prepare(pos.data_ptr(), N, views.ctypes.data, V, ws.data_ptr(), ws.numel(), main.cuda_stream))
+        state.update(pos=pos, views=views, N=N, ws=ws)
+
+    def sweep(packed, lmin, ncls, best=None):
+        labels = torch.empty(state["N"], dtype=torch.int32, device=device)
+        with torch.cuda.device(device):
+            check(L.gsl_lift_sweep(state["pos"].data_ptr(), state["N"], state["views"].ctypes.data, V,
+                                   packed.data_ptr() if V else None, int(lmin), int(ncls), labels.data_ptr(),
+                                   best.data_ptr() if best is not None else None,
+                                   state["ws"].data_ptr(), state["ws"].numel(), main.cuda_stream))
+        return labels
+
+    if V == 0 or positions.shape[0] == 0:
+        labels = np.full(positions.shape[0], -1, dtype=np.int32)
+        return (labels, np.zeros(positions.shape[0], np.uint8)) if want_near else labels
+
+    wide = False
+    if label_min is not None and n_classes is not None:
+        prepare()
+        packed = _pack_explicit(seg_maps, shapes, device, int(label_min), int(n_classes))
+        st = _Staged(packed, int(label_min), int(n_classes), int(label_min), int(label_min) + int(n_classes) - 1,
+                     4 * sum(h * w for h, w in shapes), V, 0)
+    elif world > 1:
+        st = _stage_sharded(seg_maps, shapes, device, dist, world, rank, before_wait=prepare)
+    else:
+        st = _stage_pipelined(seg_maps, shapes, device, before_wait=prepare)
+    if st.lo < st.label_min or st.hi > st.label_min + st.n_classes - 1:
+        if label_min is not None and n_classes is not None:
+            raise ValueError(f"label map value outside [{label_min}, {label_min + n_classes})")
+        wide = True
+    if not wide:
+        ncls = max(st.hi - st.label_min + 1, 1) if st.hi >= st.lo else 1      # fewer histogram rows per Gaussian
+        labels = sweep(st.packed, st.label_min, min(ncls, st.n_classes))
+    else:
+        dense, uniq = _stage_wide(seg_maps, shapes, device)
+        n_ids = int(uniq.numel())
+        labels = best = None
+        packed = torch.empty(int(ops.packed_offsets(shapes)[-1]), dtype=torch.uint8, device=device)
+        for first in range(0, n_ids, 255):
+            n_here = min(255, n_ids - first)
+            ops.pack_labels(dense, shapes, first, n_here, out=packed, check_range=False)
+            b = torch.empty(state["N"], dtype=torch.int32, device=device)       # uint32 keys, carried as int32 storage
+            lab = sweep(packed, first, n_here, best=b)
+            if labels is None:
+                labels, best = lab, b
+            else:
+                ops.lift_merge(labels, best, lab, b)
+        seen = labels >= 0
+        labels = torch.where(seen, uniq[labels.clamp(min=0).long()], labels)           # dense id -> the map's own value
+        st.h2d_bytes = 4 * sum(h * w for h, w in shapes) + st.h2d_bytes
+    last_call_stats.update(h2d_bytes=st.h2d_bytes + int(state["pos"].numel()) * 4, d2h_bytes=int(state["N"]) * 4,
+                           views_as_int32=st.views_as_int32, views_narrowed_on_host=st.views_narrowed,
+                           label_passes=1 if not wide else (n_ids + 254) // 255)
+    if trace:
+        torch.cuda.synchronize(device)
+        print(f"[gslift trace] lift_labels: staging + sweep {1e3 * (time.perf_counter() - t_enter):.2f} ms, "
+              f"{st.views_as_int32} views as int32, {st.views_narrowed} narrowed on the host", file=sys.stderr)
     if want_near:
-        return _to_host(res[0]), _to_host(res[1])
-    return _to_host(res)
+        near = ops.lift_near(state["pos"], state["views"], near_eps)
+        return _to_host(labels), _to_host(near)
+    return _to_host(labels)
+
+
+def _pack_explicit(seg_maps, shapes, device, label_min, n_classes):
+    """Upload every map as int32 and pack it with the caller's code window (raises on a value
+    outside it)."""
+    sizes = [h * w for h, w in shapes]
+    staged = torch.empty(int(sum(sizes)), dtype=torch.int32, device=device)
+    _copy_views(seg_maps, sizes, 0, len(seg_maps), staged)
+    return ops.pack_labels(staged, shapes, label_min, n_classes)
 
 
 def _to_host(t: torch.Tensor) -> np.ndarray:

@@ -47,10 +47,11 @@ _ws = _Workspace()
 # lifting
 # --------------------------------------------------------------------------------------
 def packed_map_bytes(seg_h: int, seg_w: int) -> int:
-    """Bytes of one packed (tiled) label map of seg_h x seg_w pixels (include/gslift.h)."""
-    tiles_x = (int(seg_w) + 15) // 16 + 2
-    tiles_y = (int(seg_h) + 7) // 8 + 2
-    return tiles_x * tiles_y * 128
+    """Bytes of one packed label map of seg_h x seg_w pixels (include/gslift.h: 16-pixel strips
+    plus a ring of zero codes)."""
+    strips_x = (int(seg_w) + 15) // 16 + 2
+    rows_pad = ((int(seg_h) + 7) // 8 + 2) * 8
+    return strips_x * rows_pad * 16
 
 
 def packed_offsets(map_shapes) -> np.ndarray:
@@ -153,51 +154,65 @@ def label_range(maps: torch.Tensor):
     return lo, hi
 
 
-def lift_votes(pos: torch.Tensor, views: np.ndarray, packed: torch.Tensor,
-               label_min: int = DEFAULT_LABEL_MIN, n_classes: int = DEFAULT_N_CLASSES,
-               want_near: bool = False, near_eps: float = 1e-4, view_window: int = 0,
-               out: torch.Tensor | None = None):
-    """Vote loop + majority of assign_labels (dls:255-306) on precomputed, packed maps.
-
-    pos float32 [N,3] (device), views from make_views, packed uint8 (device).
-    Returns labels int32 [N] (device); with want_near also a uint8 [N] near-boundary mask.
-    """
+def _check_lift(pos: torch.Tensor, views: np.ndarray, packed: torch.Tensor | None):
     _require_cuda(pos, "pos")
     if pos.dtype != torch.float32 or pos.dim() != 2 or pos.shape[1] != 3:
         raise TypeError("pos must be float32 [N, 3]")
     views = np.ascontiguousarray(views)
     if views.dtype != VIEW_DTYPE:
         raise TypeError("views must come from make_views")
-    V = len(views)
-    if V:
+    if len(views) and packed is not None:
         _require_cuda(packed, "packed")
         need = max(int(r["map_offset"]) + packed_map_bytes(int(r["seg_h"]), int(r["seg_w"])) for r in views)
         if packed.numel() < need:
             raise ValueError(f"packed holds {packed.numel()} bytes, views address {need}")
-    N = pos.shape[0]
+    return views
+
+
+def lift_near(pos: torch.Tensor, views: np.ndarray, near_eps: float = 1e-4) -> torch.Tensor:
+    """uint8 [N]: 1 where some (Gaussian, view) lies within near_eps of a decision edge -- the set
+    the parity criterion exempts from bit-exactness (float64, every pair)."""
+    views = _check_lift(pos, views, None)
+    N, V = pos.shape[0], len(views)
+    near = torch.empty(N, dtype=torch.uint8, device=pos.device)
+    L = lib()
+    ws = _ws.get(pos.device, L.gsl_lift_workspace_bytes(N, V))
+    with torch.cuda.device(pos.device):
+        check(L.gsl_lift_near(pos.data_ptr(), N, views.ctypes.data, V, near.data_ptr(), float(near_eps),
+                              ws.data_ptr(), ws.numel(), _stream()))
+    return near
+
+
+def lift_votes(pos: torch.Tensor, views: np.ndarray, packed: torch.Tensor,
+               label_min: int = DEFAULT_LABEL_MIN, n_classes: int = DEFAULT_N_CLASSES,
+               want_near: bool = False, near_eps: float = 1e-4,
+               out: torch.Tensor | None = None):
+    """Vote loop + majority of assign_labels (dls:255-306) on precomputed, packed maps.
+
+    pos float32 [N,3] (device), views from make_views, packed uint8 (device).
+    Returns labels int32 [N] (device); with want_near also a uint8 [N] near-boundary mask.
+    """
+    views = _check_lift(pos, views, packed)
+    N, V = pos.shape[0], len(views)
     labels = out if out is not None else torch.empty(N, dtype=torch.int32, device=pos.device)
     near = torch.empty(N, dtype=torch.uint8, device=pos.device) if want_near else None
     L = lib()
-    nbytes = L.gsl_lift_workspace_bytes(N, V)
-    ws = _ws.get(pos.device, nbytes)
+    ws = _ws.get(pos.device, L.gsl_lift_workspace_bytes(N, V))
     with torch.cuda.device(pos.device):
         check(L.gsl_lift_votes(pos.data_ptr(), N, views.ctypes.data, V,
                                packed.data_ptr() if V else None, int(label_min), int(n_classes),
                                labels.data_ptr(), near.data_ptr() if want_near else None,
-                               float(near_eps), int(view_window), ws.data_ptr(), ws.numel(), _stream()))
+                               float(near_eps), ws.data_ptr(), ws.numel(), _stream()))
     return (labels, near) if want_near else labels
 
 
 def lift_phases(pos: torch.Tensor, views: np.ndarray, packed: torch.Tensor,
                 label_min: int = DEFAULT_LABEL_MIN, n_classes: int = DEFAULT_N_CLASSES,
-                view_window: int = 0, out: torch.Tensor | None = None):
-    """lift_votes as its three ABI phases.  Returns (run_prepare, run_sweep, run_majority, labels):
-    zero-argument callables that enqueue gsl_lift_prepare (ordering + culling), gsl_lift_gather_range
-    over all views (the projection + gather sweep) and gsl_lift_majority on the current stream
-    (benchmarks put events between them)."""
-    _require_cuda(pos, "pos")
-    _require_cuda(packed, "packed")
-    views = np.ascontiguousarray(views)
+                out: torch.Tensor | None = None, best: torch.Tensor | None = None):
+    """lift_votes as its two ABI steps.  Returns (run_prepare, run_sweep, labels): zero-argument
+    callables that enqueue gsl_lift_prepare (ordering + per-tile verdicts; reads no maps) and
+    gsl_lift_sweep (projection + gather + vote + majority, one kernel) on the current stream."""
+    views = _check_lift(pos, views, packed)
     N, V = pos.shape[0], len(views)
     labels = out if out is not None else torch.empty(N, dtype=torch.int32, device=pos.device)
     L = lib()
@@ -207,14 +222,22 @@ def lift_phases(pos: torch.Tensor, views: np.ndarray, packed: torch.Tensor,
         check(L.gsl_lift_prepare(pos.data_ptr(), N, views.ctypes.data, V, ws.data_ptr(), ws.numel(), _stream()))
 
     def run_sweep():
-        check(L.gsl_lift_gather_range(pos.data_ptr(), N, views.ctypes.data, V, 0, V, packed.data_ptr(), None, 0.0,
-                                      int(view_window), ws.data_ptr(), ws.numel(), _stream()))
+        check(L.gsl_lift_sweep(pos.data_ptr(), N, views.ctypes.data, V, packed.data_ptr() if V else None,
+                               int(label_min), int(n_classes), labels.data_ptr(),
+                               best.data_ptr() if best is not None else None, ws.data_ptr(), ws.numel(), _stream()))
 
-    def run_majority():
-        check(L.gsl_lift_majority(N, V, int(label_min), int(n_classes), labels.data_ptr(),
-                                  ws.data_ptr(), ws.numel(), _stream()))
+    return run_prepare, run_sweep, labels
 
-    return run_prepare, run_sweep, run_majority, labels
+
+def lift_merge(labels: torch.Tensor, best: torch.Tensor, labels_b: torch.Tensor, best_b: torch.Tensor):
+    """In place: (labels, best) <- whichever of the two candidates has the larger vote key (more
+    votes, earlier first sighting on a tie: the reference's rule across label ranges)."""
+    for name, x in (("labels", labels), ("best", best), ("labels_b", labels_b), ("best_b", best_b)):
+        _require_cuda(x, name)
+    with torch.cuda.device(labels.device):
+        check(lib().gsl_lift_merge(labels.data_ptr(), best.data_ptr(), labels_b.data_ptr(), best_b.data_ptr(),
+                                   labels.numel(), _stream()))
+    return labels, best
 
 
 # --------------------------------------------------------------------------------------

@@ -15,8 +15,8 @@
  *     is enqueued on it; no entry point synchronises the device.
  *   - return 0 on success, a negative GSL_E* code otherwise; gsl_last_error() then returns
  *     a thread-local message.  Nothing throws, nothing calls exit().
- *   - entry points keep no global state (camera tables travel as kernel parameters), so calls
- *     on distinct streams are independent.
+ *   - entry points keep no global state besides a launch counter (tables travel through the
+ *     caller's workspace), so calls on distinct streams with distinct workspaces are independent.
  *   - there is no CPU fallback: without a CUDA device every compute entry fails with
  *     GSL_ECUDA.
  */
@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GSL_ABI_VERSION 2
+#define GSL_ABI_VERSION 3
 
 #define GSL_OK        0
 #define GSL_EINVAL   -1   /* bad argument (NULL pointer, negative size, V/K/D out of range) */
@@ -38,7 +38,7 @@ extern "C" {
 #define GSL_ECUDA    -3   /* CUDA runtime error (message carries cudaGetErrorString)        */
 #define GSL_ERANGE   -4   /* label value outside the packable range                         */
 
-#define GSL_MAX_VIEWS   65535   /* view index is kept in 16 bits by the majority kernel      */
+#define GSL_MAX_VIEWS   65535   /* view index is kept in 16 bits by the vote keys            */
 #define GSL_MAX_CODES   255     /* distinct label values per call (uint8 code 0 = "no vote") */
 #define GSL_KMEANS_MAX_K 1024
 #define GSL_KMEANS_MAX_D 256
@@ -68,6 +68,10 @@ int gsl_version(void);
 /* Message for the last non-zero return on this thread ("" if none). */
 const char *gsl_last_error(void);
 
+/* Kernels this process has launched through the library so far (statistics only: benchmarks
+ * report the difference around their timed region). */
+unsigned long long gsl_launch_count(void);
+
 /* Number of CUDA devices visible to the library, or a negative error code. */
 int gsl_device_count(void);
 
@@ -80,9 +84,9 @@ int gsl_device_count(void);
  *   maps    n_maps row-major int32 maps of seg_h x seg_w, back to back (4-byte aligned; 16-byte
  *           alignment and seg_w % 4 == 0 enable the vector path)
  *   packed  n_maps packed maps of gsl_packed_map_bytes(seg_w, seg_h) bytes each, back to back
- *           (16-byte aligned).  The packed layout is private to the library: 16 x 8-pixel tiles
- *           of 128 bytes surrounded by a ring of zero tiles, so that the 32 gathers of a warp of
- *           neighbouring Gaussians touch a few cache lines instead of one per image row.
+ *           (16-byte aligned).  The packed layout is private to the library: strips 16 pixels wide
+ *           (a 128-byte line = 16 x 8 pixels) inside a ring of zero codes, so that the 32 gathers
+ *           of a warp of neighbouring Gaussians touch a few cache lines instead of one per row.
  * Views with different map shapes are packed by separate calls; GslView.map_offset is the byte
  * offset of a view's packed map inside the buffer handed to gsl_lift_votes.
  */
@@ -108,7 +112,8 @@ int gsl_tile_codes(const uint8_t *codes, int n_maps, int seg_w, int seg_h, uint8
  * INT_MIN); lets the host choose label_min / n_classes without a CPU pass. */
 int gsl_label_range(const int32_t *maps, int64_t n_px, int *d_minmax, void *stream);
 
-/* Scratch needed by gsl_lift_votes for N Gaussians and V views. */
+/* Scratch needed by the gsl_lift_* entry points for N Gaussians and V views (about 40 bytes per
+ * Gaussian plus 2 bytes per (128-Gaussian tile, view)). */
 size_t gsl_lift_workspace_bytes(int64_t N, int V);
 
 /*
@@ -118,6 +123,8 @@ size_t gsl_lift_workspace_bytes(int64_t N, int V);
  * outcome), test z > 0 and image bounds, rescale + clamp (dls:281-286), gather the code, count; then
  * labels[i] = the label with the most votes, the one seen first in view order on a tie
  * (Python max() over an insertion-ordered dict, dls:303), or -1 if never visible (dls:306).
+ * Votes are counted inside the sweep kernel (per-Gaussian histograms in shared memory): nothing
+ * per (Gaussian, view) is ever written to device memory.
  *
  *   pos        float32 [N][3]         gaussians['position'] (dls:36-38)
  *   views      HOST array of V views in camera order, views whose image is missing already
@@ -125,41 +132,42 @@ size_t gsl_lift_workspace_bytes(int64_t N, int V);
  *   packed     uint8 codes from gsl_pack_labels, view v at packed + views[v].map_offset
  *   label_min, n_classes   the pair the maps were packed with
  *   labels     int32 [N] out
- *   near       optional uint8 [N] out (may be NULL): 1 when some (Gaussian, view) has an
- *              image coordinate within near_eps px of an integer or |z_cam| < near_eps --
- *              the set exempt from bit-exactness in the parity criterion.
- *   view_window  views per window -- the set of label maps all SMs sweep together, i.e. what L2
- *              holds at a time: <= 8 selects 8, anything else (0 = default) 16; results do not
- *              depend on it.  All windows the float32 screening covers are swept by one launch.
+ *   near       optional uint8 [N] out (may be NULL): gsl_lift_near's diagnostic
+ *
+ * gsl_lift_votes == gsl_lift_prepare then gsl_lift_sweep on the same stream and workspace.
  */
 int gsl_lift_votes(const float *pos, int64_t N, const GslView *views, int V,
                    const uint8_t *packed, int label_min, int n_classes, int32_t *labels,
-                   uint8_t *near, double near_eps, int view_window,
+                   uint8_t *near, double near_eps,
                    void *ws, size_t ws_bytes, void *stream);
 
 /*
- * The two phases of gsl_lift_votes, separately callable (same arguments, same workspace):
- * gather fills the vote sheet in `ws` (one uint8 code per (Gaussian, view)), majority reduces
- * it to labels.  gsl_lift_votes == gather then majority on the same stream.
- */
-int gsl_lift_gather(const float *pos, int64_t N, const GslView *views, int V,
-                    const uint8_t *packed, uint8_t *near, double near_eps, int view_window,
-                    void *ws, size_t ws_bytes, void *stream);
-/*
- * gsl_lift_gather in two steps, so that views can be swept while later maps are still being
- * uploaded: prepare uploads the view tables, orders the Gaussians and decides which (tile, view) pairs can be skipped (it
- * reads camera parameters only, no maps); gather_range sweeps views [v_begin, v_end), v_begin a
- * multiple of 16, whose packed maps must be resident.  gsl_lift_gather == prepare + range(0, V).
- * `near` (if used) must be zeroed by the caller before the first range.
+ * The two steps of gsl_lift_votes.  prepare reads camera parameters and positions only (no maps,
+ * so it can run while maps are still being uploaded): it uploads the view tables, sorts the
+ * Gaussians into spatial order, boxes every run of 128 and decides per (tile, view) whether the
+ * view can be skipped, swept with the tile-wide error bound, or needs the per-pair / float64
+ * treatment.  sweep needs all packed maps resident and the workspace prepare filled.
+ *   best       optional uint32 [N] out (may be NULL): votes of the winning label << 16 |
+ *              (65535 - view of its first sighting), 0 when labels[i] == -1.  Label sets wider than
+ *              GSL_MAX_CODES are lifted in several passes over disjoint label ranges and merged
+ *              with gsl_lift_merge: the larger key wins, exactly the reference's rule.
  */
 int gsl_lift_prepare(const float *pos, int64_t N, const GslView *views, int V,
                      void *ws, size_t ws_bytes, void *stream);
-int gsl_lift_gather_range(const float *pos, int64_t N, const GslView *views, int V,
-                          int v_begin, int v_end, const uint8_t *packed,
-                          uint8_t *near, double near_eps, int view_window,
-                          void *ws, size_t ws_bytes, void *stream);
-int gsl_lift_majority(int64_t N, int V, int label_min, int n_classes, int32_t *labels,
-                      const void *ws, size_t ws_bytes, void *stream);
+int gsl_lift_sweep(const float *pos, int64_t N, const GslView *views, int V,
+                   const uint8_t *packed, int label_min, int n_classes, int32_t *labels,
+                   uint32_t *best, void *ws, size_t ws_bytes, void *stream);
+/* labels[i], best[i] = the pair with the larger key of (labels, best) and (labels_b, best_b). */
+int gsl_lift_merge(int32_t *labels, uint32_t *best, const int32_t *labels_b, const uint32_t *best_b,
+                   int64_t N, void *stream);
+
+/*
+ * Diagnostic of the parity criterion: near[i] = 1 when some (Gaussian i, view) has an image
+ * coordinate within near_eps px of an integer or |z_cam| < near_eps -- the set exempt from
+ * bit-exactness.  Evaluates every pair with the float64 expressions (no culling).
+ */
+int gsl_lift_near(const float *pos, int64_t N, const GslView *views, int V, uint8_t *near,
+                  double near_eps, void *ws, size_t ws_bytes, void *stream);
 
 /* Test hook: counts (into *n_bad, device) the i for which the kernel's shared-reciprocal
  * division of a1[i]/b[i], a2[i]/b[i] differs in any bit from IEEE-754 division. */

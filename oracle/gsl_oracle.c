@@ -41,6 +41,18 @@ typedef struct {
 
 int orc_version(void) { return 1; }
 
+/* Thread count of the parallel loops below.  `torchrun` exports OMP_NUM_THREADS=1 to its workers;
+ * bench.py's reference arm sets the count from the process' CPU affinity instead, so that the CPU
+ * baseline uses the box's cores at every rank count. */
+void orc_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_max_threads(void)
 {
 #ifdef _OPENMP

@@ -263,8 +263,19 @@ def make_kmeans(km):
     print("[golden] kmeans_empty_k8: seed", seed, "clusters used", len(np.unique(lab)), "of 8")
 
 
+def make_bundled_cameras():
+    """The reference's bundled camera file (311 views of 3114 x 2075, BASELINE config C2) as a test
+    input: the GPU box has no /root/reference.  Parsed and re-serialised (repr round-trips floats)."""
+    import gzip
+    bundled = json.load(open(os.path.join(REF, "Web_Viewer_Gaussians_Selection", "cameras.json")))
+    with gzip.GzipFile(os.path.join(OUT, "bundled_cameras.json.gz"), "wb", mtime=0) as fh:
+        fh.write(json.dumps(bundled).encode())
+    print(f"[golden] bundled_cameras.json.gz: {len(bundled)} cameras")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    make_bundled_cameras()
     dls, km = load_reference()
     make_probes()
     make_lifting(dls)

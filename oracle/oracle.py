@@ -47,7 +47,8 @@ assert VIEW_DTYPE.itemsize == 176
 
 def build(force: bool = False) -> str:
     """Compile the C oracle if it is missing (or `force`)."""
-    if force or not os.path.exists(_LIB_PATH):
+    src = os.path.join(_HERE, "gsl_oracle.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(src) > os.path.getmtime(_LIB_PATH):
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return _LIB_PATH
 
@@ -63,6 +64,8 @@ def lib() -> ctypes.CDLL:
         i64, i32, vp, dbl = ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_double
         L.orc_version.restype = i32
         L.orc_max_threads.restype = i32
+        L.orc_set_threads.argtypes = [i32]
+        L.orc_set_threads.restype = None
         L.orc_translation.argtypes = [vp, vp, vp]
         L.orc_translation.restype = None
         L.orc_project.argtypes = [vp, vp, vp, vp]
@@ -83,6 +86,18 @@ def lib() -> ctypes.CDLL:
 
 def max_threads() -> int:
     return int(lib().orc_max_threads())
+
+
+def set_threads(n: int | None = None) -> int:
+    """Use `n` OpenMP threads (default: every core this process may run on, whatever
+    OMP_NUM_THREADS says -- torchrun sets it to 1).  Returns the count in effect."""
+    if n is None:
+        try:
+            n = len(os.sched_getaffinity(0))
+        except (AttributeError, OSError):
+            n = os.cpu_count() or 1
+    lib().orc_set_threads(int(n))
+    return max_threads()
 
 
 def _ptr(a: np.ndarray):

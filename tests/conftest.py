@@ -13,13 +13,12 @@ def pytest_configure(config):
 
 
 def pytest_sessionstart(session):
-    """Build libgslift.so (nvcc, sm_100a) and the C oracle if they are missing, e.g. on a fresh
-    checkout: both are git-ignored build products.  A stale-but-present library is left alone
-    here (the GPU box receives the prebuilt files and may have no reason to rebuild)."""
+    """Build libgslift.so (nvcc, sm_100a) and the C oracle when they are missing or OLDER than
+    any of their sources (both are git-ignored build products; the GPU box receives the prebuilt
+    files together with the sources, so an up-to-date library is not rebuilt there)."""
     import importlib
     builder = importlib.import_module("3d_gaussian_splatting_project_b200.build")
-    if not os.path.exists(builder.LIB):
-        builder.build()
+    builder.build()                 # no-op unless stale()
     from oracle import oracle as orc
     orc.build()
 

@@ -30,7 +30,7 @@ def test_library_is_built_and_exports_every_declared_symbol():
 
 def test_version_and_view_struct_size():
     native = pkg("_native")
-    assert native.lib().gsl_version() == 2
+    assert native.lib().gsl_version() == native.ABI_VERSION == 3
     hdr = open(os.path.join(ROOT, "include", "gslift.h")).read()
     assert "176 bytes" in hdr and native.VIEW_DTYPE.itemsize == 176
 
@@ -39,7 +39,7 @@ def test_workspace_queries_are_host_only():
     L = pkg("_native").lib()
     assert L.gsl_lift_workspace_bytes(0, 0) >= 0
     n = L.gsl_lift_workspace_bytes(1000, 10)
-    assert n >= 3 * 1024 * 4                     # ceil(10/4) words x Npad(1024) x 4 B
+    assert n >= 1024 * (12 + 4)                  # sorted positions + permutation
     assert L.gsl_lift_workspace_bytes(1000, 300) > n
     assert L.gsl_kmeans_workspace_bytes(100000, 59, 64) >= 64 * 60 * 8
 
@@ -50,7 +50,7 @@ def test_argument_validation_needs_no_device():
     assert L.gsl_pack_labels(None, 1, 8, 8, None, -1, 255, None, None) == -1
     assert L.gsl_packed_map_bytes(1920, 1080) == 122 * 137 * 128 and L.gsl_packed_map_bytes(0, 5) == 0
     assert b"null" in L.gsl_last_error()
-    assert L.gsl_lift_votes(None, -1, None, 0, None, -1, 255, None, None, 0.0, 0, None, 0, None) == -1
+    assert L.gsl_lift_votes(None, -1, None, 0, None, -1, 255, None, None, 0.0, None, 0, None) == -1
     assert L.gsl_kmeans_assign(None, 10, 0, None, 4, None, None, 0, None) == -1
     assert L.gsl_kmeans_assign(None, 10, 3, None, 4000, None, None, 0, None) == -1
     with pytest.raises(native.GslError):
@@ -101,7 +101,7 @@ int main(void)
     if (gsl_version() != GSL_ABI_VERSION) return 3;
     if (gsl_packed_map_bytes(1920, 1080) != 122LL * 137 * 128) return 4;
     if (gsl_kmeans_exchange_bytes(8, 59, 64) != 256 + 2u * 8 * 64 * 60 * 8) return 5;
-    if (gsl_lift_votes(NULL, -1, NULL, 0, NULL, -1, 255, NULL, NULL, 0.0, 0, NULL, 0, NULL) != GSL_EINVAL) return 6;
+    if (gsl_lift_votes(NULL, -1, NULL, 0, NULL, -1, 255, NULL, NULL, 0.0, NULL, 0, NULL) != GSL_EINVAL) return 6;
     if (strlen(gsl_last_error()) == 0) return 7;
     printf("abi ok %d\n", gsl_version());
     return 0;
@@ -113,4 +113,4 @@ int main(void)
                          "-L", lib_dir, "-lgslift", f"-Wl,-rpath,{lib_dir}"], capture_output=True, text=True)
     assert cc.returncode == 0, cc.stderr
     run = subprocess.run([str(exe)], capture_output=True, text=True)
-    assert run.returncode == 0 and "abi ok 2" in run.stdout, (run.returncode, run.stdout, run.stderr)
+    assert run.returncode == 0 and "abi ok 3" in run.stdout, (run.returncode, run.stdout, run.stderr)

@@ -64,9 +64,11 @@ def test_lifting_script_c2(oracle, tmp_path):
         np.save(seg_dir / f"{cam['img_name']}_segmap.npy", m)
     out = subprocess.run([sys.executable, os.path.join(ROOT, "deep_learning_segmentation.py"), "--ply_file", str(src),
                           "--camera_file", str(tmp_path / "cameras.json"), "--input_dir", str(img_dir),
-                          "--output_dir", str(seg_dir), "--output_file", str(dst)], capture_output=True, text=True, cwd=ROOT)
+                          "--output_dir", str(seg_dir), "--output_file", str(dst)], capture_output=True, text=True, cwd=ROOT,
+                         env=dict(os.environ, GSLIFT_REUSE_SEGMAPS="1"))        # reuse of segment_image's files is opt-in
     assert out.returncode == 0, out.stderr[-2000:]
     assert "Loading cameras..." in out.stdout and "Label statistics:" in out.stdout
+    assert out.stdout.count("Using precomputed segmentation map") == len(c["cameras"])
     assert out.stdout.count("Processing image") == len(c["cameras"])
     back = plyio.read_ply(dst)
     assert not back.text and back["vertex"].data.dtype.names[-1] == "label"

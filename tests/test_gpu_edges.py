@@ -20,16 +20,16 @@ def test_abi_error_codes_on_device():
     labels = torch.empty(10, dtype=torch.int32, device=DEV)
     ws = torch.empty(64, dtype=torch.uint8, device=DEV)
     rc = L.gsl_lift_votes(pos.data_ptr(), 10, views.ctypes.data, 3, packed.data_ptr(), -1, 255, labels.data_ptr(),
-                          None, 0.0, 0, ws.data_ptr(), ws.numel(), None)
+                          None, 0.0, ws.data_ptr(), ws.numel(), None)
     assert rc == -2 and b"workspace" in L.gsl_last_error()                      # GSL_EWORKSPACE
     big = torch.empty(L.gsl_lift_workspace_bytes(10, 3), dtype=torch.uint8, device=DEV)
     rc = L.gsl_lift_votes(pos.data_ptr(), 10, views.ctypes.data, 3, packed.data_ptr(), -1, 256, labels.data_ptr(),
-                          None, 0.0, 0, big.data_ptr(), big.numel(), None)
+                          None, 0.0, big.data_ptr(), big.numel(), None)
     assert rc == -1 and b"n_classes" in L.gsl_last_error()                      # GSL_EINVAL
     bad = views.copy()
     bad["seg_w"][1] = 0
     rc = L.gsl_lift_votes(pos.data_ptr(), 10, bad.ctypes.data, 3, packed.data_ptr(), -1, 255, labels.data_ptr(),
-                          None, 0.0, 0, big.data_ptr(), big.numel(), None)
+                          None, 0.0, big.data_ptr(), big.numel(), None)
     assert rc == -1 and b"view 1" in L.gsl_last_error()
     maps = torch.zeros(1024 + 1, dtype=torch.int32, device=DEV)
     err = torch.zeros(1, dtype=torch.int32, device=DEV)
@@ -37,9 +37,9 @@ def test_abi_error_codes_on_device():
     assert rc == -1 and b"aligned" in L.gsl_last_error()
     rc = L.gsl_pack_labels(maps.data_ptr(), 1, 0, 32, packed.data_ptr(), -1, 255, err.data_ptr(), None)
     assert rc == -1 and b"shape" in L.gsl_last_error()
-    rc = L.gsl_lift_gather_range(pos.data_ptr(), 10, views.ctypes.data, 3, 8, 3, packed.data_ptr(), None, 0.0, 0,
-                                 big.data_ptr(), big.numel(), None)
-    assert rc == -1 and b"view range" in L.gsl_last_error()
+    rc = L.gsl_lift_sweep(pos.data_ptr(), 10, views.ctypes.data, 3, None, -1, 255, labels.data_ptr(), None,
+                          big.data_ptr(), big.numel(), None)
+    assert rc == -1 and b"null packed" in L.gsl_last_error()
     with pytest.raises(native.GslError, match="shared memory"):
         ops.kmeans_assign(torch.zeros(100, 200, device=DEV), torch.zeros(900, 200, device=DEV))
     with pytest.raises(TypeError):
@@ -126,7 +126,7 @@ def test_screened_sweep_equals_float64_sweep_on_random_configs(oracle, seed, mon
         else:                                           # rescaled
             shapes.append((int(rng.integers(10, 300)), int(rng.integers(10, 400)))); sizes.append((int(rng.integers(20, 500)), int(rng.integers(20, 500))))
     if seed % 2:
-        cams[3]["width"] = cams[3]["width"] + 0.5       # non-integer frame: its window takes the float64 kernel
+        cams[3]["width"] = cams[3]["width"] + 0.5       # non-integer frame: the view takes the float64 path
     maps = [rng.integers(-1, 150, size=s).astype(np.int32) for s in shapes]
     pos = (rng.standard_normal((30_000, 3)) * rng.uniform(0.5, 3.0)).astype(np.float32)
     flat = np.concatenate([m.reshape(-1) for m in maps])
@@ -138,6 +138,8 @@ def test_screened_sweep_equals_float64_sweep_on_random_configs(oracle, seed, mon
     monkeypatch.setenv("GSLIFT_LIFT_F64", "1")
     got64 = ops.lift_votes(d_pos, views, packed).cpu().numpy()
     monkeypatch.delenv("GSLIFT_LIFT_F64")
-    got8 = ops.lift_votes(d_pos, views, packed, view_window=8).cpu().numpy()
-    assert np.array_equal(got, got64) and np.array_equal(got, got8)
+    monkeypatch.setenv("GSLIFT_LIFT_ORDER", "0")
+    got_plain = ops.lift_votes(d_pos, views, packed).cpu().numpy()
+    monkeypatch.delenv("GSLIFT_LIFT_ORDER")
+    assert np.array_equal(got, got64) and np.array_equal(got, got_plain)
     assert np.array_equal(got, want), f"{(got != want).sum()} labels differ from the oracle"
