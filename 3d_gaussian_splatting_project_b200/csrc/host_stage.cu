@@ -135,22 +135,18 @@ extern "C" int gsl_host_pack_labels(const int32_t *const *maps, const int64_t *n
 namespace gsl {
 
 // One thread per 16-byte row of the output, a warp = 4 adjacent strips x 8 rows (same mapping as
-// pack_labels_kernel in lift.cu): 8 runs of 64 consecutive codes in, four 128-byte lines out.
+// pack_labels_kernel in lift.cu): 8 runs of 64 consecutive codes in, four 128-byte lines and their
+// eight coarse cells out.
 __global__ void __launch_bounds__(256)
 tile_codes_kernel(const uint8_t *__restrict__ codes, uint8_t *__restrict__ packed, int n_maps, int seg_w, int seg_h,
                   uint32_t strips_x, uint32_t rows_pad, int64_t total, int vec_ok)
 {
-    const uint32_t groups_x = (strips_x + 3u) >> 2, groups_y = rows_pad >> 3;
-    const int64_t per_map = (int64_t)groups_x * groups_y * 32;
-    const int64_t map_rows = (int64_t)strips_x * rows_pad;
+    const int64_t fine_bytes = map_fine_bytes(seg_w, seg_h), map_bytes = fine_bytes + map_coarse_bytes(seg_w, seg_h);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const int64_t m = i / per_map;
-        const uint32_t rem = (uint32_t)(i - m * per_map);
-        const uint32_t grp = rem >> 5, lane = rem & 31u;
-        const uint32_t gy = grp / groups_x, gx = grp - gy * groups_x;
-        const uint32_t strip = gx * 4u + (lane >> 3), row = gy * 8u + (lane & 7u);
-        if (strip >= strips_x) continue;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {      // total % 32 == 0: warps stay whole
+        int64_t m;
+        uint32_t strip, row;
+        pack_coords(i, strips_x, rows_pad, m, strip, row);
         const int y = (int)row - 8, x0 = (int)(strip * 16) - 16;
         uint4 w = make_uint4(0u, 0u, 0u, 0u);
         if (y >= 0 && y < seg_h && x0 >= 0 && x0 < seg_w) {
@@ -164,7 +160,7 @@ tile_codes_kernel(const uint8_t *__restrict__ codes, uint8_t *__restrict__ packe
                 w = make_uint4(v[0], v[1], v[2], v[3]);
             }
         }
-        reinterpret_cast<uint4 *>(packed)[m * map_rows + (int64_t)strip * rows_pad + row] = w;
+        store_packed_row(packed, map_bytes, fine_bytes, m, strips_x, rows_pad, strip, row, w, strip < strips_x);
     }
 }
 

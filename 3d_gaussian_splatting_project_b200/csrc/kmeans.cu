@@ -239,7 +239,9 @@ kmeans_finalize_kernel(const double *__restrict__ sums, const float *__restrict_
 // seq grows by one per call; slots alternate by its parity.  That is enough: a rank can only be
 // one exchange ahead of a peer (to start exchange s + 1 it needs that peer's flag for s), so
 // the data of exchange s is never overwritten before exchange s + 2, by which time every rank has
-// finished reading s.  The wait is bounded (2 s): on a time-out the shift comes back NaN.
+// finished reading s.  The wait is bounded (GSLIFT_EXCHANGE_TIMEOUT_MS, default 30 s -- ranks of a
+// job are lined up by a barrier before their first exchange, k_means.lloyd): on a time-out the
+// shift comes back NaN.
 // ---------------------------------------------------------------------------------------
 constexpr int kMaxRanks = 16;
 constexpr size_t kXchgFlags = 128, kXchgSlots = 256;
@@ -267,7 +269,7 @@ __device__ __forceinline__ unsigned long long global_ns()
 
 __global__ void __launch_bounds__(kReduceThreads)
 kmeans_exchange_kernel(const double *__restrict__ partials, int n_parts, int n_el, PeerTable peers, int rank, int world,
-                       unsigned long long seq, const float *__restrict__ old_c, int K, int D,
+                       unsigned long long seq, unsigned long long timeout_ns, const float *__restrict__ old_c, int K, int D,
                        float *__restrict__ new_c, float *__restrict__ shift, double *__restrict__ sums)
 {
     __shared__ double part[32][33];
@@ -301,7 +303,7 @@ kmeans_exchange_kernel(const double *__restrict__ partials, int n_parts, int n_e
         const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(peers.base[rank] + kXchgFlags) + threadIdx.x;
         const unsigned long long t0 = global_ns();
         while (ld_acquire_sys(mine) < seq)
-            if (global_ns() - t0 > 2000000000ull) { s_timeout = 1; break; }
+            if (global_ns() - t0 > timeout_ns) { s_timeout = 1; break; }
     }
     __syncthreads();
     const double *slots = reinterpret_cast<const double *>(peers.base[rank] + kXchgSlots + (size_t)(seq & 1ull) * world * (size_t)n_el * sizeof(double));
@@ -484,8 +486,11 @@ extern "C" int gsl_kmeans_step_exchange(const float *data, int64_t N, int D, con
         grid = step_grid(N);
         if (int rc = launch_step<true>(data, N, D, centroids, K, labels, partials, grid, st)) return rc;
     }
+    // how long a rank waits inside the kernel for its peers (milliseconds)
+    const char *tmo = getenv("GSLIFT_EXCHANGE_TIMEOUT_MS");
+    const unsigned long long timeout_ns = (unsigned long long)((tmo && atof(tmo) > 0 ? atof(tmo) : 30000.0) * 1e6);
     kmeans_exchange_kernel<<<(n_el + 31) / 32, kReduceThreads, 0, st>>>(partials, grid, n_el, peers, rank, world, (unsigned long long)seq,
-                                                              centroids, K, D, new_centroids, shift, sums);
+                                                              timeout_ns, centroids, K, D, new_centroids, shift, sums);
     GSL_LAUNCH_CHECK("kmeans_exchange_kernel");
     return GSL_OK;
 }

@@ -26,7 +26,8 @@ constexpr int kOrdTile = 1024;
 constexpr int kOrdThreads = 256;
 
 __global__ void __launch_bounds__(kOrdThreads)
-ordered_count_kernel(const int32_t *__restrict__ labels, int64_t N, int K, int32_t *__restrict__ tile_counts)
+ordered_count_kernel(const int32_t *__restrict__ labels, int64_t N, int K, int32_t *__restrict__ tile_counts,
+                     int *__restrict__ bad_label)
 {
     extern __shared__ int hist[];
     for (int i = threadIdx.x; i < K; i += kOrdThreads) hist[i] = 0;
@@ -34,7 +35,11 @@ ordered_count_kernel(const int32_t *__restrict__ labels, int64_t N, int K, int32
     const int64_t row0 = (int64_t)blockIdx.x * kOrdTile;
     for (int r = threadIdx.x; r < kOrdTile; r += kOrdThreads) {
         const int64_t row = row0 + r;
-        if (row < N) atomicAdd(&hist[labels[row]], 1);
+        if (row < N) {
+            const int lab = labels[row];
+            if ((unsigned)lab < (unsigned)K) atomicAdd(&hist[lab], 1);
+            else *bad_label = 1;                         // skipped here and in the scatter; the shift comes back NaN
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < K; i += kOrdThreads) tile_counts[(size_t)blockIdx.x * K + i] = hist[i];
@@ -90,6 +95,7 @@ ordered_scatter_kernel(const int32_t *__restrict__ labels, int64_t N, int K,
     for (int c = 0; c < 4; ++c) {
         const int64_t row = row0 + c * 32 + lane;
         lab[c] = row < N ? labels[row] : -1;
+        if ((unsigned)lab[c] >= (unsigned)K) lab[c] = -1;        // out-of-range labels belong to no cluster
         if (lab[c] >= 0) atomicAdd(&wc[w * K + lab[c]], 1);
     }
     __syncthreads();
@@ -221,7 +227,8 @@ ordered_chain_kernel(const float *__restrict__ data, int D, const int32_t *__res
 }
 
 __global__ void __launch_bounds__(256)
-shift_kernel(const float *__restrict__ a, const float *__restrict__ b, int n, float *__restrict__ shift)
+shift_kernel(const float *__restrict__ a, const float *__restrict__ b, int n, float *__restrict__ shift,
+             const int *__restrict__ bad_label)
 {
     __shared__ double red[8];
     double sq = 0.0;
@@ -235,7 +242,7 @@ shift_kernel(const float *__restrict__ a, const float *__restrict__ b, int n, fl
     if (threadIdx.x == 0) {
         double s = 0.0;
         for (int w = 0; w < 8; ++w) s += red[w];
-        *shift = (float)sqrt(s);
+        *shift = (bad_label && *bad_label) ? __int_as_float(0x7fc00000) : (float)sqrt(s);
     }
 }
 
@@ -277,12 +284,14 @@ extern "C" int gsl_kmeans_update_ordered(const float *data, const int32_t *label
     int64_t *start = reinterpret_cast<int64_t *>(base + L.start - 256);
     int32_t *members = reinterpret_cast<int32_t *>(base + L.members - 256);
     const int n_tiles = (int)((N + kOrdTile - 1) / kOrdTile);
+    int *bad_label = reinterpret_cast<int *>(base);          // first word of the workspace header
+    GSL_CUDA_TRY(cudaMemsetAsync(bad_label, 0, sizeof(int), st));
 
     if (N == 0) {
         GSL_CUDA_TRY(cudaMemsetAsync(total, 0, sizeof(int64_t) * (size_t)K, st));
         GSL_CUDA_TRY(cudaMemsetAsync(start, 0, sizeof(int64_t) * (size_t)K, st));
     } else {
-        ordered_count_kernel<<<n_tiles, kOrdThreads, K * sizeof(int), st>>>(labels, N, K, tile_counts);
+        ordered_count_kernel<<<n_tiles, kOrdThreads, K * sizeof(int), st>>>(labels, N, K, tile_counts, bad_label);
         GSL_LAUNCH_CHECK("ordered_count_kernel");
         ordered_scan_kernel<<<K, kOrdThreads, 0, st>>>(tile_counts, n_tiles, K, total);
         GSL_LAUNCH_CHECK("ordered_scan_kernel");
@@ -298,7 +307,7 @@ extern "C" int gsl_kmeans_update_ordered(const float *data, const int32_t *label
     dim3 grid((unsigned)K, (unsigned)((D + 31) / 32));
     ordered_chain_kernel<<<grid, kOrdThreads, ch_smem, st>>>(data, D, members, start, total, old_centroids, new_centroids);
     GSL_LAUNCH_CHECK("ordered_chain_kernel");
-    shift_kernel<<<1, 256, 0, st>>>(new_centroids, old_centroids, K * D, shift);
+    shift_kernel<<<1, 256, 0, st>>>(new_centroids, old_centroids, K * D, shift, bad_label);
     GSL_LAUNCH_CHECK("shift_kernel");
     return GSL_OK;
 }

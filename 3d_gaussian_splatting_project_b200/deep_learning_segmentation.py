@@ -248,7 +248,7 @@ def _stage_pipelined(seg_maps, shapes, device, before_wait=None):
 
     The first uploads are enqueued before anything else happens on the host; `before_wait` (the
     Gaussian ordering, which reads no maps) is called right after them.  Codes are label + 2
-    (label_min = -1, 255 codes); the caller checks the value range and re-stages when the labels do
+    (label_min = -1, 254 codes); the caller checks the value range and re-stages when the labels do
     not fit that window."""
     import ctypes
     import time
@@ -301,7 +301,7 @@ def _stage_pipelined(seg_maps, shapes, device, before_wait=None):
             check(L.gsl_label_range(buf.data_ptr(), n_px[ci], minmax.data_ptr(), main.cuda_stream))
             for v, n in _runs(shapes, v0, v1):
                 check(L.gsl_pack_labels(buf.data_ptr() + 4 * int(starts[v] - starts[v0]), n, shapes[v][1], shapes[v][0],
-                                        packed.data_ptr() + int(pstarts[v]), -1, 255, err.data_ptr(), main.cuda_stream))
+                                        packed.data_ptr() + int(pstarts[v]), -1, ops.DEFAULT_N_CLASSES, err.data_ptr(), main.cuda_stream))
             slot_free[ci % 2] = torch.cuda.Event()
             slot_free[ci % 2].record(main)
             if ci + 2 < n_dev:
@@ -339,7 +339,7 @@ def _stage_pipelined(seg_maps, shapes, device, before_wait=None):
                 npx = (ctypes.c_int64 * len(keep))(*[sizes[v] for v in range(vb0, vb1)])
                 off0, off1 = int(starts[vb0] - starts[hv0]), int(starts[vb1] - starts[hv0])
                 t0 = time.perf_counter()
-                check(L.gsl_host_pack_labels(ptrs, npx, len(keep), -1, 255, pinned.data_ptr() + off0, _host_cores(), host_mm, ctypes.byref(bad)))
+                check(L.gsl_host_pack_labels(ptrs, npx, len(keep), -1, ops.DEFAULT_N_CLASSES, pinned.data_ptr() + off0, _host_cores(), host_mm, ctypes.byref(bad)))
                 t_narrow += time.perf_counter() - t0
                 px_narrow += off1 - off0
                 with torch.cuda.stream(copy):
@@ -357,7 +357,7 @@ def _stage_pipelined(seg_maps, shapes, device, before_wait=None):
         dev_px = int(starts[chunks[n_dev]] if n_dev < len(chunks) else starts[V])
         lo, hi = (int(x) for x in minmax.tolist())           # synchronises: every copy has been consumed
         lo, hi = min(lo, int(host_mm[0])), max(hi, int(host_mm[1]))
-    return _Staged(packed, -1, 255, lo, hi, 4 * dev_px + int(starts[V] - dev_px), min(n_dev * CH, V), V - min(n_dev * CH, V))
+    return _Staged(packed, -1, ops.DEFAULT_N_CLASSES, lo, hi, 4 * dev_px + int(starts[V] - dev_px), min(n_dev * CH, V), V - min(n_dev * CH, V))
 
 
 def _stage_sharded(seg_maps, shapes, device, dist, world, rank, before_wait=None):
@@ -431,7 +431,7 @@ def _stage_sharded(seg_maps, shapes, device, dist, world, rank, before_wait=None
             check(L.gsl_label_range(buf.data_ptr(), n_px[ci], minmax.data_ptr(), main.cuda_stream))
             for v, n in _runs(shapes, v0, v1):
                 check(L.gsl_pack_labels(buf.data_ptr() + 4 * int(starts[v] - starts[v0]), n, shapes[v][1], shapes[v][0],
-                                        packed.data_ptr() + int(pstarts[v]), -1, 255, err.data_ptr(), main.cuda_stream))
+                                        packed.data_ptr() + int(pstarts[v]), -1, ops.DEFAULT_N_CLASSES, err.data_ptr(), main.cuda_stream))
             slot_free[ci % 2] = torch.cuda.Event()
             slot_free[ci % 2].record(main)
             if ci + 2 < len(chunks):
@@ -457,7 +457,7 @@ def _stage_sharded(seg_maps, shapes, device, dist, world, rank, before_wait=None
                 if b > a:
                     dist.broadcast(packed[a:b], src=r)
         lo, hi = int(mm[0].item()), -int(mm[1].item())
-    return _Staged(packed, -1, 255, lo, hi, 4 * int(starts[v_hi] - starts[v_lo]), V, 0)
+    return _Staged(packed, -1, ops.DEFAULT_N_CLASSES, lo, hi, 4 * int(starts[v_hi] - starts[v_lo]), V, 0)
 
 
 _push_streams = {}
@@ -471,9 +471,9 @@ def _push_stream(device):
 
 
 def _stage_wide(seg_maps, shapes, device):
-    """Label sets that do not fit one 255-code window (reference dls:288-295 accepts any int32
+    """Label sets that do not fit one 254-code window (reference dls:288-295 accepts any int32
     label): all maps go to the device as int32 and every value is replaced by its rank among the
-    distinct values (dense ids), which the caller then lifts in passes of 255 ids.  Returns
+    distinct values (dense ids), which the caller then lifts in passes of 254 ids.  Returns
     (dense int32 maps flat, sorted distinct values)."""
     sizes = [h * w for h, w in shapes]
     staged = torch.empty(int(sum(sizes)), dtype=torch.int32, device=device)
@@ -490,7 +490,7 @@ def lift_labels(positions, cameras, seg_maps, image_sizes=None, device=None, wan
     positions   float32 [N,3] array or tensor (under torch.distributed: THIS rank's Gaussians)
     cameras     camera dicts, in voting order
     seg_maps    list of int arrays [seg_h, seg_w] (NumPy or tensors), one per camera; any int32
-                label values (more than 255 distinct values are lifted in several passes)
+                label values (more than 254 distinct values are lifted in several passes)
     image_sizes per camera (orig_w, orig_h); default = the map's own size (scale 1.0)
     label_min, n_classes  optional explicit code window (values outside it raise)
     Returns int32 NumPy labels (and the near-boundary mask when want_near).
@@ -559,8 +559,9 @@ def lift_labels(positions, cameras, seg_maps, image_sizes=None, device=None, wan
         n_ids = int(uniq.numel())
         labels = best = None
         packed = torch.empty(int(ops.packed_offsets(shapes)[-1]), dtype=torch.uint8, device=device)
-        for first in range(0, n_ids, 255):
-            n_here = min(255, n_ids - first)
+        P = ops.DEFAULT_N_CLASSES
+        for first in range(0, n_ids, P):
+            n_here = min(P, n_ids - first)
             ops.pack_labels(dense, shapes, first, n_here, out=packed, check_range=False)
             b = torch.empty(state["N"], dtype=torch.int32, device=device)       # uint32 keys, carried as int32 storage
             lab = sweep(packed, first, n_here, best=b)
@@ -573,7 +574,7 @@ def lift_labels(positions, cameras, seg_maps, image_sizes=None, device=None, wan
         st.h2d_bytes = 4 * sum(h * w for h, w in shapes) + st.h2d_bytes
     last_call_stats.update(h2d_bytes=st.h2d_bytes + int(state["pos"].numel()) * 4, d2h_bytes=int(state["N"]) * 4,
                            views_as_int32=st.views_as_int32, views_narrowed_on_host=st.views_narrowed,
-                           label_passes=1 if not wide else (n_ids + 254) // 255)
+                           label_passes=1 if not wide else -(-n_ids // ops.DEFAULT_N_CLASSES))
     if trace:
         torch.cuda.synchronize(device)
         print(f"[gslift trace] lift_labels: staging + sweep {1e3 * (time.perf_counter() - t_enter):.2f} ms, "

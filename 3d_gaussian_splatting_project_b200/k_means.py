@@ -18,8 +18,9 @@ Semantics kept from the reference (line numbers are the reference's):
             bit-identical centroids, hence identical trajectories;
   "fast"    float64 segmented sums, shardable; centroids agree with the reference to its own
             float32 rounding (about 1e-5 relative on clusters of 1e5 members).
-Under torch.distributed (world size > 1) each rank passes ITS rows and `update` is forced to
-"fast"; the partial sums and counts are exchanged inside the reduction kernel over peer memory
+Under torch.distributed (world size > 1) `lloyd` is the sharded entry point: each rank passes ITS
+rows and the SAME centroids, and `update` is forced to "fast" (the reference entry points broadcast
+rank 0's initial draw before they call it); the partial sums and counts are exchanged inside the reduction kernel over peer memory
 (ops.KMeansExchange -> gsl_kmeans_step_exchange).  GSLIFT_KMEANS_EXCHANGE=nccl selects the
 three-step form instead (reduce kernel, NCCL all-reduce of K x (D+1) float64, finalize kernel),
 which is also what is used when torch cannot set up symmetric memory on the machine.
@@ -77,11 +78,22 @@ def _make_exchange(centroids, dist):
     return _exchanges[key]
 
 
+_LOOKAHEAD = 2      # iterations enqueued before the shift of an earlier one is read back (lloyd)
+
+
 def lloyd(data, centroids, max_iter=100, tol=1e-4, update=None, verbose=True, device=None):
     """The iteration shared by both reference entry points, on device tensors.
 
     data float32 [N,D] (this rank's rows), centroids float32 [K,D] (replicated).
-    Returns (centroids, labels int32 device tensor, iterations run)."""
+    Returns (centroids, labels int32 device tensor, iterations run).
+
+    The device never waits for the host: every iteration's shift (km:131) travels to a pinned
+    host word asynchronously and is read -- and printed, in order -- `GSLIFT_LLOYD_LOOKAHEAD`
+    (default 2) iterations later, while the next iterations are already enqueued.  When an
+    earlier iteration turns out to have converged, the iterations enqueued past it are simply
+    discarded: the reference breaks BEFORE adopting the new centroids (km:132-136), so the result
+    is the centroid set that iteration was given.  Under torch.distributed every rank sees the same
+    shifts and makes the same decisions, so all ranks issue the same exchanges."""
     dist = _dist_world()
     if update is None:
         update = os.environ.get("GSLIFT_KMEANS_UPDATE", "ordered")
@@ -92,10 +104,39 @@ def lloyd(data, centroids, max_iter=100, tol=1e-4, update=None, verbose=True, de
     labels = torch.empty(data.shape[0], dtype=torch.int32, device=data.device)
     sums = torch.empty((centroids.shape[0], centroids.shape[1] + 1), dtype=torch.float64, device=data.device)
     exchange = _make_exchange(centroids, dist) if update == "fast" else None
-    done = 0
-    for iteration in range(max_iter):
+    if exchange is not None and exchange.world > 1:
+        # ranks may arrive seconds apart (I/O, garbage collection); the in-kernel exchange waits for
+        # peers with a bounded spin, so line the ranks up before the first one
+        dist.barrier()
+    depth = max(int(os.environ.get("GSLIFT_LLOYD_LOOKAHEAD", _LOOKAHEAD)), 0)
+    pinned = torch.empty(depth + 1, dtype=torch.float32, pin_memory=True)
+    stream = torch.cuda.current_stream(data.device)
+    pending = []                     # (iteration, centroids it was given, centroids it produced, pinned slot, event)
+    done, final = 0, None
+
+    def settle(entry):
+        """Read one iteration's shift; True when it converged (km:131-136)."""
+        nonlocal done, final
+        iteration, given, produced, slot, ev = entry
+        ev.synchronize()
+        shift_value = np.float32(pinned[slot].item())
+        if exchange is not None and exchange.world > 1 and np.isnan(shift_value):
+            raise RuntimeError("K-means exchange returned a NaN shift: a rank did not reach the exchange within the time-out "
+                               "(GSLIFT_EXCHANGE_TIMEOUT_MS; every rank must call lloyd with the same max_iter/tol), or the data is not finite")
+        done = iteration + 1
         if verbose:
             print(iteration)
+            print(shift_value)
+        if shift_value < tol:
+            if verbose:
+                print(f"Converged after {iteration + 1} iterations.")
+            final = given
+            return True
+        final = produced
+        return False
+
+    converged = False
+    for iteration in range(max_iter):
         if exchange is not None:
             new_centroids, shift = exchange.step(data, centroids, labels)
         elif update == "fast":
@@ -106,20 +147,22 @@ def lloyd(data, centroids, max_iter=100, tol=1e-4, update=None, verbose=True, de
         else:
             ops.kmeans_assign(data, centroids, labels)
             new_centroids, shift = ops.kmeans_update_ordered(data, labels, centroids)
-        shift_value = np.float32(shift.item())
-        if exchange is not None and exchange.world > 1 and np.isnan(shift_value):
-            raise RuntimeError("K-means exchange returned a NaN shift: a rank did not reach the exchange within "
-                               "2 s (every rank must call lloyd with the same max_iter/tol), or the data is not finite")
-        done = iteration + 1
-        if verbose:
-            print(shift_value)
-        if shift_value < tol:
-            if verbose:
-                print(f"Converged after {iteration + 1} iterations.")
-            break
+        slot = iteration % (depth + 1)
+        pinned[slot:slot + 1].copy_(shift, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        pending.append((iteration, centroids, new_centroids, slot, ev))
         centroids = new_centroids
-    ops.kmeans_assign(data, centroids, labels)
-    return centroids, labels, done
+        while len(pending) > depth and not converged:
+            converged = settle(pending.pop(0))
+        if converged:
+            break
+    while pending and not converged:
+        converged = settle(pending.pop(0))
+    if final is None:                                       # max_iter == 0
+        final = centroids
+    ops.kmeans_assign(data, final, labels)
+    return final, labels, done
 
 
 def _run(data_np, k, colors, max_iter, tol, palette_scale, update):
@@ -128,7 +171,13 @@ def _run(data_np, k, colors, max_iter, tol, palette_scale, update):
     start = data_np[np.random.choice(N, k, replace=False)]
     device = torch.device("cuda")
     data = torch.from_numpy(data_np).to(device)
-    centroids, labels, _ = lloyd(data, torch.from_numpy(start).to(device), max_iter, tol, update)
+    start_dev = torch.from_numpy(start).to(device)
+    dist = _dist_world()
+    if dist is not None:
+        # lloyd() needs the SAME centroids on every rank; each rank drew from its own rows and its
+        # own NumPy stream, so rank 0's draw is the one everybody uses
+        dist.broadcast(start_dev, src=0)
+    centroids, labels, _ = lloyd(data, start_dev, max_iter, tol, update)
     palette = (np.array(COLORS) / 255.0 if palette_scale else np.array(COLORS)).astype(np.float32)
     if colors.dtype == np.float32:
         colors_dev = torch.from_numpy(np.ascontiguousarray(colors)).to(device)

@@ -11,7 +11,7 @@ import torch
 from ._native import VIEW_DTYPE, check, lib
 
 DEFAULT_LABEL_MIN = -1      # YOLO background / Mask2Former "no segment" (dls:101)
-DEFAULT_N_CLASSES = 255     # codes 1..255; covers ADE20K (150) and COCO (80) ids plus -1
+DEFAULT_N_CLASSES = 254     # codes 1..254 (GSL_MAX_CODES); covers ADE20K (150) and COCO (80) ids plus -1
 
 
 def _require_cuda(t: torch.Tensor, name: str) -> None:
@@ -48,10 +48,11 @@ _ws = _Workspace()
 # --------------------------------------------------------------------------------------
 def packed_map_bytes(seg_h: int, seg_w: int) -> int:
     """Bytes of one packed label map of seg_h x seg_w pixels (include/gslift.h: 16-pixel strips
-    plus a ring of zero codes)."""
+    plus a ring of zero codes, followed by the coarse table of 8 x 8-pixel cells)."""
     strips_x = (int(seg_w) + 15) // 16 + 2
     rows_pad = ((int(seg_h) + 7) // 8 + 2) * 8
-    return strips_x * rows_pad * 16
+    coarse = (2 * strips_x * (rows_pad // 8) + 15) // 16 * 16        # one byte per 8 x 8-pixel cell
+    return strips_x * rows_pad * 16 + coarse
 
 
 def packed_offsets(map_shapes) -> np.ndarray:
@@ -353,8 +354,10 @@ class KMeansExchange:
         return new, shift
 
 
-def kmeans_update_ordered(data: torch.Tensor, labels: torch.Tensor, old: torch.Tensor):
-    """Reference-order float32 sequential mean (km:125-128 bit for bit).  Single device."""
+def kmeans_update_ordered(data: torch.Tensor, labels: torch.Tensor, old: torch.Tensor, validate: bool = False):
+    """Reference-order float32 sequential mean (km:125-128 bit for bit).  Single device.
+    Labels outside [0, K) are skipped by the kernels and turn the shift into NaN; validate=True
+    waits for the result and raises GslError(GSL_ERANGE) in that case."""
     N, D, K = _check_kmeans(data, old)
     _require_cuda(labels, "labels")
     if labels.dtype != torch.int32 or labels.numel() != N:
@@ -366,6 +369,9 @@ def kmeans_update_ordered(data: torch.Tensor, labels: torch.Tensor, old: torch.T
     with torch.cuda.device(data.device):
         check(L.gsl_kmeans_update_ordered(data.data_ptr(), labels.data_ptr(), N, D, K, old.data_ptr(),
                                           new.data_ptr(), shift.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+    if validate and bool(torch.isnan(shift).item()) and bool(((labels < 0) | (labels >= K)).any().item()):
+        from ._native import GslError
+        raise GslError(-4, f"gsl_kmeans_update_ordered: a label lies outside [0, {K})")
     return new, shift
 
 

@@ -39,7 +39,8 @@ extern "C" {
 #define GSL_ERANGE   -4   /* label value outside the packable range                         */
 
 #define GSL_MAX_VIEWS   65535   /* view index is kept in 16 bits by the vote keys            */
-#define GSL_MAX_CODES   255     /* distinct label values per call (uint8 code 0 = "no vote") */
+#define GSL_MAX_CODES   254     /* distinct label values per call (uint8 code 0 = "no vote",
+                                   255 = the coarse table's "mixed cell" marker)             */
 #define GSL_KMEANS_MAX_K 1024
 #define GSL_KMEANS_MAX_D 256
 
@@ -217,7 +218,7 @@ int gsl_kmeans_finalize(const double *sums, const float *old_centroids, int K, i
  *           ranks.  Every rank must make the call (it is a collective); a rank with N == 0 joins
  *           with zero sums.
  *   sums    float64 [K][D+1] out: the totals over all ranks.
- *   shift   NaN if another rank did not arrive within 2 s.
+ *   shift   NaN if another rank did not arrive within GSLIFT_EXCHANGE_TIMEOUT_MS (default 30 s).
  */
 size_t gsl_kmeans_exchange_bytes(int world, int D, int K);
 int gsl_kmeans_step_exchange(const float *data, int64_t N, int D, const float *centroids, int K,
@@ -229,7 +230,8 @@ int gsl_kmeans_step_exchange(const float *data, int64_t N, int D, const float *c
  * Reference-order update (km:125-128 exactly): every centroid coordinate is the float32
  * SEQUENTIAL sum of its members in index order, divided in float64 and rounded to float32
  * -- what NumPy's mean(axis=0) produces.  Single device only (the order cannot be sharded).
- *   labels int32 [N] from gsl_kmeans_assign / gsl_kmeans_step.
+ *   labels int32 [N] from gsl_kmeans_assign / gsl_kmeans_step.  A label outside [0, K) is skipped
+ *   and reported: *shift comes back NaN (the call is asynchronous, so there is no return code for it).
  */
 int gsl_kmeans_update_ordered(const float *data, const int32_t *labels, int64_t N, int D, int K,
                               const float *old_centroids, float *new_centroids, float *shift,

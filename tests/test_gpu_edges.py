@@ -19,25 +19,25 @@ def test_abi_error_codes_on_device():
     packed = torch.zeros(3 * ops.packed_map_bytes(48, 64), dtype=torch.uint8, device=DEV)
     labels = torch.empty(10, dtype=torch.int32, device=DEV)
     ws = torch.empty(64, dtype=torch.uint8, device=DEV)
-    rc = L.gsl_lift_votes(pos.data_ptr(), 10, views.ctypes.data, 3, packed.data_ptr(), -1, 255, labels.data_ptr(),
+    rc = L.gsl_lift_votes(pos.data_ptr(), 10, views.ctypes.data, 3, packed.data_ptr(), -1, 254, labels.data_ptr(),
                           None, 0.0, ws.data_ptr(), ws.numel(), None)
     assert rc == -2 and b"workspace" in L.gsl_last_error()                      # GSL_EWORKSPACE
     big = torch.empty(L.gsl_lift_workspace_bytes(10, 3), dtype=torch.uint8, device=DEV)
-    rc = L.gsl_lift_votes(pos.data_ptr(), 10, views.ctypes.data, 3, packed.data_ptr(), -1, 256, labels.data_ptr(),
+    rc = L.gsl_lift_votes(pos.data_ptr(), 10, views.ctypes.data, 3, packed.data_ptr(), -1, 255, labels.data_ptr(),
                           None, 0.0, big.data_ptr(), big.numel(), None)
     assert rc == -1 and b"n_classes" in L.gsl_last_error()                      # GSL_EINVAL
     bad = views.copy()
     bad["seg_w"][1] = 0
-    rc = L.gsl_lift_votes(pos.data_ptr(), 10, bad.ctypes.data, 3, packed.data_ptr(), -1, 255, labels.data_ptr(),
+    rc = L.gsl_lift_votes(pos.data_ptr(), 10, bad.ctypes.data, 3, packed.data_ptr(), -1, 254, labels.data_ptr(),
                           None, 0.0, big.data_ptr(), big.numel(), None)
     assert rc == -1 and b"view 1" in L.gsl_last_error()
     maps = torch.zeros(1024 + 1, dtype=torch.int32, device=DEV)
     err = torch.zeros(1, dtype=torch.int32, device=DEV)
-    rc = L.gsl_pack_labels(maps.data_ptr() + 2, 1, 32, 32, packed.data_ptr(), -1, 255, err.data_ptr(), None)
+    rc = L.gsl_pack_labels(maps.data_ptr() + 2, 1, 32, 32, packed.data_ptr(), -1, 254, err.data_ptr(), None)
     assert rc == -1 and b"aligned" in L.gsl_last_error()
-    rc = L.gsl_pack_labels(maps.data_ptr(), 1, 0, 32, packed.data_ptr(), -1, 255, err.data_ptr(), None)
+    rc = L.gsl_pack_labels(maps.data_ptr(), 1, 0, 32, packed.data_ptr(), -1, 254, err.data_ptr(), None)
     assert rc == -1 and b"shape" in L.gsl_last_error()
-    rc = L.gsl_lift_sweep(pos.data_ptr(), 10, views.ctypes.data, 3, None, -1, 255, labels.data_ptr(), None,
+    rc = L.gsl_lift_sweep(pos.data_ptr(), 10, views.ctypes.data, 3, None, -1, 254, labels.data_ptr(), None,
                           big.data_ptr(), big.numel(), None)
     assert rc == -1 and b"null packed" in L.gsl_last_error()
     with pytest.raises(native.GslError, match="shared memory"):

@@ -24,7 +24,10 @@ def test_make_views_matches_oracle_table(oracle):
             assert np.array_equal(mine[name], ref[name]), name     # incl. t = -R @ p, bit for bit
     ops = pkg("ops")
     offs = ops.packed_offsets(c["shapes"])
-    assert np.array_equal(mine["map_offset"], offs[:-1]) and ops.packed_map_bytes(1080, 1920) == 122 * 137 * 128
+    L = pkg("_native").lib()
+    for (h, w) in [(1080, 1920), (1038, 1557), (1, 1), (77, 51), (2075, 3114)]:       # host formula == the library's
+        assert ops.packed_map_bytes(h, w) == L.gsl_packed_map_bytes(w, h)
+    assert np.array_equal(mine["map_offset"], offs[:-1]) and ops.packed_map_bytes(1080, 1920) == 122 * 137 * 128 + 33440
     assert mine["scale_x"][0] == 1.0 and mine["width"][0] == 3114
 
 
@@ -171,12 +174,12 @@ def test_host_label_narrowing_matches_numpy():
 
     for n in (0, 1, 31, 32, 33, 1000, 123457):
         a = rng.integers(-5, 300, n).astype(np.int32)
-        got, mm, bad = run([a], -1, 255, 0)
+        got, mm, bad = run([a], -1, 254, 0)
         c = a.astype(np.int64) + 1
-        want = np.where((c >= 0) & (c < 255), c + 1, 0).astype(np.uint8)
+        want = np.where((c >= 0) & (c < 254), c + 1, 0).astype(np.uint8)
         assert np.array_equal(got, want), n
         if n:
-            assert mm == (int(a.min()), int(a.max())) and bad == int(((c < 0) | (c >= 255)).any())
+            assert mm == (int(a.min()), int(a.max())) and bad == int(((c < 0) | (c >= 254)).any())
     maps = [rng.integers(-1, 150, s).astype(np.int32) for s in (70001, 5, 300000, 64, 0, 131072)]
     for nt in (1, 3, 5, 8):
         got, mm, bad = run(maps, -1, 151, nt)
@@ -184,4 +187,4 @@ def test_host_label_narrowing_matches_numpy():
     ext = np.array([-2**31, 2**31 - 1, 0, 7], np.int32)           # wrap-around of v - label_min must not alias a valid code
     got, mm, bad = run([ext], 5, 10, 1)
     assert got.tolist() == [0, 0, 0, 3] and bad == 1 and mm == (-2**31, 2**31 - 1)
-    assert L.gsl_host_pack_labels(None, None, 1, -1, 255, None, 0, None, None) == -1
+    assert L.gsl_host_pack_labels(None, None, 1, -1, 254, None, 0, None, None) == -1
