@@ -45,4 +45,12 @@ bool tc_supported(int D, int K);
 int launch_step_tc(bool accumulate, const float *data, int64_t N, int D, const float *centroids, int K,
                    int32_t *labels, double *partials, int grid, cudaStream_t st);
 
+// kmeans_umma.cu: the same screening with tcgen05.mma / tensor memory, full 128-row tiles of a
+// 16-byte aligned matrix.  *rows_done = rows covered (0: not applicable), *n_parts = partial blocks written.
+bool umma_supported(int D, int K);
+int launch_step_umma(bool accumulate, const float *data, int64_t N, int D, const float *centroids, int K,
+                     int32_t *labels, double *partials, cudaStream_t st, int64_t *rows_done, int *n_parts);
+int launch_umma_selftest(const float *data, int64_t N, int D, const float *centroids, int K, int32_t *labels,
+                         unsigned long long *out2, cudaStream_t st, int64_t *rows_done);
+
 }  // namespace gsl

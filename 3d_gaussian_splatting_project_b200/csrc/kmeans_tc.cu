@@ -27,6 +27,7 @@
 
 #include "common.cuh"
 #include "kmeans_common.cuh"
+#include "kmeans_screen.cuh"
 
 namespace gsl {
 
@@ -34,8 +35,6 @@ constexpr int kTcThreads = 256;          // 8 warps x 32 rows
 constexpr int kTcRows = 256;
 constexpr int kTcKP = 64;                // centroids padded to 64 (8 n-tiles)
 constexpr int kTcCPitch = 68;            // c' row pitch: 68 % 32 == 4 -> conflict-free B fragments
-constexpr int kTcPairs = 32;             // (row, candidate) pairs a warp refines cooperatively per tile;
-                                         // 32 * (4 + 2) B fit in the warp's 32 candidate-mask slots, which they reuse
 
 struct TcSmem {
     size_t acc, cprime, cn2, nc, mean, tile, lab, mask, bar, total;
@@ -62,50 +61,11 @@ static inline TcSmem tc_layout(int D, int K, bool accumulate)
     return s;
 }
 
-__device__ __forceinline__ uint32_t to_tf32(float x)
-{
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
-
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
 {
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
-// ---- TMA 1-D bulk copy of a whole tile (global -> shared), completion on an mbarrier ----
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(void *bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-
-// One thread: order prior generic-proxy accesses to the buffer before the async-proxy write,
-// arm the barrier with the byte count and launch the copy.
-__device__ __forceinline__ void bulk_load_tile(void *dst, const void *src, unsigned bytes, void *bar)
-{
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
-__device__ __forceinline__ void mbar_wait(void *bar, unsigned parity)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
 // Stage A for the 32 rows of one warp.  On return, for mt in {0,1}, h in {0,1}: row
@@ -167,118 +127,6 @@ __device__ __forceinline__ void screen_warp(ScreenOut &o, const float *__restric
         for (int j = 0; j < 8; ++j)
 #pragma unroll
             for (int c = 0; c < 4; ++c) o.g[mt][j][c] = cn2[8 * j + 2 * t + (c & 1)] - 2.f * o.g[mt][j][c];
-}
-
-// E_k = 1.5 * 2^-9 |x'| |c'_k| + 2^-22 (|x'| + |c'_k|)^2, evaluated as an upper bound with
-// (a + b)^2 <= 2 a^2 + 2 b^2:   E_k <= |x'| * ea_k + eb_k + 2^-21 |x'|^2,
-// ea_k = 1.5 * 2^-9 |c'_k| and eb_k = 2^-21 |c'_k|^2 tabulated per centroid.
-__device__ __forceinline__ float screen_bound(float nx, float nx_term, float ea, float eb)
-{
-    return fmaf(nx, ea, eb) + nx_term;
-}
-
-// Stages B and C for one row: candidates given as a bit mask over k.
-__device__ __forceinline__ int refine_row(unsigned long long mask, const float *__restrict__ x,
-                                          const float *__restrict__ centroids, int D, float eps)
-{
-    if (__popcll(mask) == 1) return __ffsll((long long)mask) - 1;
-    float s1 = INFINITY, s2 = INFINITY;
-    int k1 = 0;
-    for (unsigned long long m = mask; m; m &= m - 1) {
-        const int k = __ffsll((long long)m) - 1;
-        const float *c = centroids + (size_t)k * D;
-        float s = 0.f;
-        for (int d = 0; d < D; ++d) {
-            const float df = x[d] - __ldg(c + d);
-            s = fmaf(df, df, s);
-        }
-        if (s < s1) { s2 = s1; s1 = s; k1 = k; }
-        else if (s < s2) s2 = s;
-    }
-    if ((s2 * (1.f - eps) > s1 * (1.f + eps)) && (s1 > 1e-30f)) return k1;
-    const float bound = s1 * (1.f + 2.f * eps);
-    double best = INFINITY;
-    int mine = 0;                                    // the float64 scan starts from (inf, 0) and needs d2 < best
-    for (unsigned long long m = mask; m; m &= m - 1) {
-        const int k = __ffsll((long long)m) - 1;
-        const float *c = centroids + (size_t)k * D;
-        float s = 0.f;
-        for (int d = 0; d < D; ++d) {
-            const float df = x[d] - __ldg(c + d);
-            s = fmaf(df, df, s);
-        }
-        if (!(s * (1.f - 2.f * eps) <= bound) && (s1 > 1e-30f)) continue;
-        const double d2 = sqdist_scipy(c, x, D);
-        if (d2 < best) { best = d2; mine = k; }
-    }
-    return mine;
-}
-
-__device__ __forceinline__ float sqdist_f32(const float *__restrict__ x, const float *__restrict__ c, int D)
-{
-    float s = 0.f;
-    for (int d = 0; d < D; ++d) {
-        const float df = x[d] - __ldg(c + d);
-        s = fmaf(df, df, s);
-    }
-    return s;
-}
-
-// Stages B and C for the 32 rows of a warp (lane = row).  Rows with one candidate are done.  The
-// (row, candidate) pairs of the others are pooled and dealt out one per lane, so the float32
-// distances cost one pass over D for the whole warp instead of one pass per candidate of the
-// unluckiest lane.  Falls back to refine_row when the pool would overflow.
-__device__ __forceinline__ int refine_warp(unsigned long long mask, const float *__restrict__ xt, int pitch,
-                                           const float *__restrict__ centroids, int D, float eps,
-                                           unsigned short *__restrict__ pair, float *__restrict__ dist, int lane)
-{
-    const int n = __popcll(mask);
-    const int want = n > 1 ? n : 0;
-    int incl = want;
-    for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-    }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    if (total == 0) return __ffsll((long long)mask) - 1;                 // whole warp decided by stage A
-    if (total > kTcPairs) return refine_row(mask, xt + lane * pitch, centroids, D, eps);
-    const int off = incl - want;
-    if (want) {
-        int i = off;
-        for (unsigned long long m = mask; m; m &= m - 1) pair[i++] = (unsigned short)((lane << 8) | (__ffsll((long long)m) - 1));
-    }
-    __syncwarp();
-    for (int p = lane; p < total; p += 32) {
-        const unsigned pr = pair[p];
-        dist[p] = sqdist_f32(xt + (pr >> 8) * pitch, centroids + (size_t)(pr & 0xffu) * D, D);
-    }
-    __syncwarp();
-    int mine = __ffsll((long long)mask) - 1;
-    if (want) {
-        float s1 = INFINITY, s2 = INFINITY;
-        int k1 = 0;
-        for (int i = off; i < off + want; ++i) {
-            const float s = dist[i];
-            const int k = pair[i] & 0xffu;
-            if (s < s1) { s2 = s1; s1 = s; k1 = k; }
-            else if (s < s2) s2 = s;
-        }
-        if ((s2 * (1.f - eps) > s1 * (1.f + eps)) && (s1 > 1e-30f)) {
-            mine = k1;
-        } else {                                                          // float64, near ties only
-            const float bound = s1 * (1.f + 2.f * eps);
-            double best = INFINITY;
-            mine = 0;                                                     // the float64 scan starts from (inf, 0)
-            for (int i = off; i < off + want; ++i) {
-                if (!(dist[i] * (1.f - 2.f * eps) <= bound) && (s1 > 1e-30f)) continue;
-                const int k = pair[i] & 0xffu;
-                const double d2 = sqdist_scipy(centroids + (size_t)k * D, xt + lane * pitch, D);
-                if (d2 < best) { best = d2; mine = k; }
-            }
-        }
-    }
-    __syncwarp();
-    return mine;
 }
 
 template <bool kAccumulate, bool kCheck>
@@ -491,6 +339,13 @@ extern "C" int gsl_kmeans_screen_selftest(const float *data, int64_t N, int D, c
     if (!data || !centroids || !labels || !out2 || N < 0) return fail(GSL_EINVAL, "gsl_kmeans_screen_selftest: bad argument");
     if (!tc_supported(D, K)) return fail(GSL_EINVAL, "gsl_kmeans_screen_selftest: needs K <= 64 and 8 <= D <= 64");
     if (N == 0) return GSL_OK;
+    // full 128-row tiles through the tcgen05 kernel (unless GSLIFT_KMEANS_UMMA=0), the rest through mma.sync
+    int64_t done = 0;
+    const char *e = getenv("GSLIFT_KMEANS_UMMA");
+    if (!(e && e[0] == '0'))
+        if (int rc = launch_umma_selftest(data, N, D, centroids, K, labels, out2, (cudaStream_t)stream, &done)) return rc;
+    if (done == N) return GSL_OK;
+    data += done * D; labels += done; N -= done;
     const int64_t tiles = (N + kTcRows - 1) / kTcRows;
     const int64_t cap = (int64_t)sm_count() * 2;
     return launch_tc_t<false, true>(data, N, D, centroids, K, labels, nullptr, (int)(tiles < cap ? tiles : cap), out2, (cudaStream_t)stream);

@@ -8,8 +8,8 @@
 namespace gsl {
 
 constexpr int kLiftThreads = 64;       // threads of a sweep CTA
-constexpr int kLiftPer = 2;            // Gaussians per thread (one packed float32x2 pair)
-constexpr int kTile = kLiftThreads * kLiftPer;    // Gaussians per tile == per sweep CTA
+constexpr int kLiftPer = 4;            // Gaussians per thread (two packed float32x2 pairs)
+constexpr int kTile = kLiftThreads * kLiftPer;    // Gaussians per tile == per sweep CTA == vote-sheet tile
 constexpr int kWin = 16;               // views per window (staging unit of the view table)
 
 // ---------------------------------------------------------------------------------------
@@ -142,7 +142,7 @@ constexpr unsigned kVerdictCull = 0u, kVerdictF64 = 65534u, kVerdictGeneral = 65
 
 // Byte offsets of the pieces of the lifting workspace (each 256-byte aligned).
 struct OrderWs {
-    size_t pos_sorted, perm, keys, keys_sorted, idx, sort_temp, sort_temp_bytes, stats, tilebox, verdict, views, facts, hot, planes, bytes;
+    size_t sheet, pos_sorted, perm, keys, keys_sorted, idx, sort_temp, sort_temp_bytes, stats, tilebox, verdict, views, facts, hot, planes, bytes;
 };
 
 OrderWs order_layout(int64_t N, int V);

@@ -19,7 +19,7 @@
 //                         code; non-finite positions take the last key
 //   sort_cells            (key, row) pairs by key (lift_sort.cu)
 //   order_permute_kernel  pos_sorted[i] = pos[perm[i]]
-//   order_tilebox_kernel  bounding box (+ non-finite flag) of each run of 128 sorted Gaussians
+//   order_tilebox_kernel  bounding box (+ non-finite flag) of each run of 256 sorted Gaussians
 //   order_planes_kernel   per view, the five half-spaces of the visibility test as linear forms
 //   order_verdict_kernel  16 bits per (tile, view): cull / fast with its bound / general / exact
 // The order inside a cell follows the input order (the sort is stable), so the whole ordering is
@@ -150,19 +150,17 @@ order_iota_kernel(int32_t *__restrict__ perm, int64_t N)
 }
 
 __global__ void __launch_bounds__(256)
-order_permute_kernel(const float *__restrict__ pos, int64_t N, const int32_t *__restrict__ perm, float *__restrict__ pos_sorted)
+order_permute_kernel(const float *__restrict__ pos, int64_t N, const int32_t *__restrict__ perm, float4 *__restrict__ pos_sorted)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     const int64_t s = perm[i];
-    pos_sorted[3 * i + 0] = pos[3 * s + 0];
-    pos_sorted[3 * i + 1] = pos[3 * s + 1];
-    pos_sorted[3 * i + 2] = pos[3 * s + 2];
+    pos_sorted[i] = make_float4(pos[3 * s + 0], pos[3 * s + 1], pos[3 * s + 2], 0.f);     // one 16-byte load per Gaussian in the sweep
 }
 
 // One warp per tile of kTile sorted Gaussians: box[tile] = {lo xyz, hi xyz, nonfinite, 0}.
 __global__ void __launch_bounds__(256)
-order_tilebox_kernel(const float *__restrict__ pos_sorted, int64_t N, int64_t n_tiles, float *__restrict__ box)
+order_tilebox_kernel(const float4 *__restrict__ pos_sorted, int64_t N, int64_t n_tiles, float *__restrict__ box)
 {
     const int64_t tile = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -172,9 +170,11 @@ order_tilebox_kernel(const float *__restrict__ pos_sorted, int64_t N, int64_t n_
     for (int r = lane; r < kTile; r += 32) {
         const int64_t g = tile * kTile + r;
         if (g >= N) break;
+        const float4 p4 = pos_sorted[g];
+        const float pv[3] = {p4.x, p4.y, p4.z};
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            const float v = pos_sorted[3 * g + a];
+            const float v = pv[a];
             if (fabsf(v) < INFINITY) { lo[a] = fminf(lo[a], v); hi[a] = fmaxf(hi[a], v); } else bad = 1;
         }
     }
@@ -309,7 +309,8 @@ OrderWs order_layout(int64_t N, int V)
     const int64_t v_pad = (V + kWin - 1) / kWin * kWin;
     size_t off = 0;
     auto take = [&](size_t bytes) { const size_t at = off; off += align_up(bytes, 256); return at; };
-    o.pos_sorted = take((size_t)n_pad * 3 * sizeof(float));
+    o.sheet = take((size_t)((V + 3) / 4) * (size_t)n_pad * sizeof(uint32_t));
+    o.pos_sorted = take((size_t)n_pad * sizeof(float4));
     o.perm = take((size_t)n_pad * sizeof(int32_t));
     o.keys = take((size_t)n_pad * sizeof(uint32_t));
     o.keys_sorted = take((size_t)n_pad * sizeof(uint32_t));
@@ -332,7 +333,7 @@ OrderWs order_layout(int64_t N, int V)
 // already in the workspace (gsl_lift_prepare).
 int order_gaussians(const float *pos, int64_t N, int V, bool sort, bool exact_only, unsigned char *base, const OrderWs &L, cudaStream_t st)
 {
-    float *pos_sorted = reinterpret_cast<float *>(base + L.pos_sorted);
+    float4 *pos_sorted = reinterpret_cast<float4 *>(base + L.pos_sorted);
     int32_t *perm = reinterpret_cast<int32_t *>(base + L.perm);
     uint32_t *keys = reinterpret_cast<uint32_t *>(base + L.keys);
     uint32_t *keys_sorted = reinterpret_cast<uint32_t *>(base + L.keys_sorted);

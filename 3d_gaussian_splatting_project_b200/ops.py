@@ -210,9 +210,12 @@ def lift_votes(pos: torch.Tensor, views: np.ndarray, packed: torch.Tensor,
 def lift_phases(pos: torch.Tensor, views: np.ndarray, packed: torch.Tensor,
                 label_min: int = DEFAULT_LABEL_MIN, n_classes: int = DEFAULT_N_CLASSES,
                 out: torch.Tensor | None = None, best: torch.Tensor | None = None):
-    """lift_votes as its two ABI steps.  Returns (run_prepare, run_sweep, labels): zero-argument
-    callables that enqueue gsl_lift_prepare (ordering + per-tile verdicts; reads no maps) and
-    gsl_lift_sweep (projection + gather + vote + majority, one kernel) on the current stream."""
+    """lift_votes as its ABI steps.  Returns (run_prepare, run_gather, run_majority, run_sweep, labels):
+    zero-argument callables that enqueue gsl_lift_prepare (ordering + per-tile verdicts; reads no
+    maps), gsl_lift_gather (projection + visibility + gather into the vote sheet) and
+    gsl_lift_majority on the current stream (benchmarks put events between them); run_sweep is
+    gsl_lift_sweep = gather + majority with the majority of one chunk of Gaussians overlapping the
+    sweep of the next (what lift_votes runs)."""
     views = _check_lift(pos, views, packed)
     N, V = pos.shape[0], len(views)
     labels = out if out is not None else torch.empty(N, dtype=torch.int32, device=pos.device)
@@ -222,12 +225,20 @@ def lift_phases(pos: torch.Tensor, views: np.ndarray, packed: torch.Tensor,
     def run_prepare():
         check(L.gsl_lift_prepare(pos.data_ptr(), N, views.ctypes.data, V, ws.data_ptr(), ws.numel(), _stream()))
 
+    def run_gather():
+        check(L.gsl_lift_gather(pos.data_ptr(), N, views.ctypes.data, V, packed.data_ptr() if V else None,
+                                ws.data_ptr(), ws.numel(), _stream()))
+
+    def run_majority():
+        check(L.gsl_lift_majority(N, V, int(label_min), int(n_classes), labels.data_ptr(),
+                                  best.data_ptr() if best is not None else None, ws.data_ptr(), ws.numel(), _stream()))
+
     def run_sweep():
         check(L.gsl_lift_sweep(pos.data_ptr(), N, views.ctypes.data, V, packed.data_ptr() if V else None,
                                int(label_min), int(n_classes), labels.data_ptr(),
                                best.data_ptr() if best is not None else None, ws.data_ptr(), ws.numel(), _stream()))
 
-    return run_prepare, run_sweep, labels
+    return run_prepare, run_gather, run_majority, run_sweep, labels
 
 
 def lift_merge(labels: torch.Tensor, best: torch.Tensor, labels_b: torch.Tensor, best_b: torch.Tensor):

@@ -113,8 +113,8 @@ int gsl_tile_codes(const uint8_t *codes, int n_maps, int seg_w, int seg_h, uint8
  * INT_MIN); lets the host choose label_min / n_classes without a CPU pass. */
 int gsl_label_range(const int32_t *maps, int64_t n_px, int *d_minmax, void *stream);
 
-/* Scratch needed by the gsl_lift_* entry points for N Gaussians and V views (about 40 bytes per
- * Gaussian plus 2 bytes per (128-Gaussian tile, view)). */
+/* Scratch needed by the gsl_lift_* entry points for N Gaussians and V views (the vote sheet, one
+ * byte per (Gaussian, view), plus about 40 bytes per Gaussian and 2 bytes per (256-Gaussian tile, view)). */
 size_t gsl_lift_workspace_bytes(int64_t N, int V);
 
 /*
@@ -124,8 +124,6 @@ size_t gsl_lift_workspace_bytes(int64_t N, int V);
  * outcome), test z > 0 and image bounds, rescale + clamp (dls:281-286), gather the code, count; then
  * labels[i] = the label with the most votes, the one seen first in view order on a tie
  * (Python max() over an insertion-ordered dict, dls:303), or -1 if never visible (dls:306).
- * Votes are counted inside the sweep kernel (per-Gaussian histograms in shared memory): nothing
- * per (Gaussian, view) is ever written to device memory.
  *
  *   pos        float32 [N][3]         gaussians['position'] (dls:36-38)
  *   views      HOST array of V views in camera order, views whose image is missing already
@@ -135,7 +133,8 @@ size_t gsl_lift_workspace_bytes(int64_t N, int V);
  *   labels     int32 [N] out
  *   near       optional uint8 [N] out (may be NULL): gsl_lift_near's diagnostic
  *
- * gsl_lift_votes == gsl_lift_prepare then gsl_lift_sweep on the same stream and workspace.
+ * gsl_lift_votes == gsl_lift_prepare, gsl_lift_gather, gsl_lift_majority on the same stream and
+ * workspace.
  */
 int gsl_lift_votes(const float *pos, int64_t N, const GslView *views, int V,
                    const uint8_t *packed, int label_min, int n_classes, int32_t *labels,
@@ -145,7 +144,7 @@ int gsl_lift_votes(const float *pos, int64_t N, const GslView *views, int V,
 /*
  * The two steps of gsl_lift_votes.  prepare reads camera parameters and positions only (no maps,
  * so it can run while maps are still being uploaded): it uploads the view tables, sorts the
- * Gaussians into spatial order, boxes every run of 128 and decides per (tile, view) whether the
+ * Gaussians into spatial order, boxes every run of 256 and decides per (tile, view) whether the
  * view can be skipped, swept with the tile-wide error bound, or needs the per-pair / float64
  * treatment.  sweep needs all packed maps resident and the workspace prepare filled.
  *   best       optional uint32 [N] out (may be NULL): votes of the winning label << 16 |
@@ -158,6 +157,15 @@ int gsl_lift_prepare(const float *pos, int64_t N, const GslView *views, int V,
 int gsl_lift_sweep(const float *pos, int64_t N, const GslView *views, int V,
                    const uint8_t *packed, int label_min, int n_classes, int32_t *labels,
                    uint32_t *best, void *ws, size_t ws_bytes, void *stream);
+/*
+ * The two kernels of gsl_lift_sweep, separately callable (benchmarks time them one by one):
+ * gather fills the vote sheet in `ws` (one uint8 code per (Gaussian, view), 4 views to a word),
+ * majority reduces it to labels.
+ */
+int gsl_lift_gather(const float *pos, int64_t N, const GslView *views, int V,
+                    const uint8_t *packed, void *ws, size_t ws_bytes, void *stream);
+int gsl_lift_majority(int64_t N, int V, int label_min, int n_classes, int32_t *labels, uint32_t *best,
+                      void *ws, size_t ws_bytes, void *stream);
 /* labels[i], best[i] = the pair with the larger key of (labels, best) and (labels_b, best_b). */
 int gsl_lift_merge(int32_t *labels, uint32_t *best, const int32_t *labels_b, const uint32_t *best_b,
                    int64_t N, void *stream);
