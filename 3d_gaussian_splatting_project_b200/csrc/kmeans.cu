@@ -403,11 +403,14 @@ static bool allow_tc()
     return !(e && e[0] == '0');
 }
 
-// GSLIFT_KMEANS_UMMA=0 keeps the mma.sync screening kernel where the tcgen05 one applies (A/B tests).
+// GSLIFT_KMEANS_UMMA=1 selects the tcgen05 screening kernel (kmeans_umma.cu) where it applies.  It
+// returns the same labels (tests run both) but is the slower of the two as measured in round 2
+// (1.77 - 1.99 ms per iteration at 6 M x 59, K = 64, against 1.19 ms for the mma.sync kernel with
+// two CTAs per SM: profiles/r2/ncu_kmeans_umma_*.txt), so it is opt-in.
 static bool allow_umma()
 {
     const char *e = getenv("GSLIFT_KMEANS_UMMA");
-    return !(e && e[0] == '0');
+    return e && e[0] == '1';
 }
 
 // One assignment pass (+ per-CTA partial sums when kAcc).  *n_parts = partial blocks written.

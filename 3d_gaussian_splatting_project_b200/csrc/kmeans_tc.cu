@@ -339,10 +339,10 @@ extern "C" int gsl_kmeans_screen_selftest(const float *data, int64_t N, int D, c
     if (!data || !centroids || !labels || !out2 || N < 0) return fail(GSL_EINVAL, "gsl_kmeans_screen_selftest: bad argument");
     if (!tc_supported(D, K)) return fail(GSL_EINVAL, "gsl_kmeans_screen_selftest: needs K <= 64 and 8 <= D <= 64");
     if (N == 0) return GSL_OK;
-    // full 128-row tiles through the tcgen05 kernel (unless GSLIFT_KMEANS_UMMA=0), the rest through mma.sync
+    // with GSLIFT_KMEANS_UMMA=1: full 128-row tiles through the tcgen05 kernel, the rest through mma.sync
     int64_t done = 0;
     const char *e = getenv("GSLIFT_KMEANS_UMMA");
-    if (!(e && e[0] == '0'))
+    if (e && e[0] == '1')
         if (int rc = launch_umma_selftest(data, N, D, centroids, K, labels, out2, (cudaStream_t)stream, &done)) return rc;
     if (done == N) return GSL_OK;
     data += done * D; labels += done; N -= done;

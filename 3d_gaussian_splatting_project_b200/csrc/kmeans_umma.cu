@@ -89,6 +89,21 @@ __device__ __forceinline__ void mbar_wait_u(void *bar, unsigned parity)
         "DONE_%=:\n\t"
         "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// same, for a thread that may wait long (the producer): back off between polls
+__device__ __forceinline__ void mbar_wait_backoff(void *bar, unsigned parity)
+{
+    unsigned done = 0;
+    for (;;) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(64);
+    }
+}
 __device__ __forceinline__ void mbar_arrive(void *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -148,6 +163,61 @@ __device__ __forceinline__ void tmem_load_row64(uint32_t taddr, float (&v)[64])
     for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Per-cluster sums of one sorted tile, walking ROWS instead of clusters: with 128 rows and up to 64
+// clusters a cluster has two members on average, so a loop per cluster is mostly overhead.  Warp w
+// takes the clusters whose first sorted row lies in [32 w, 32 w + 32): whole clusters, contiguous
+// sorted rows, about 32 of them, and no cluster is shared between warps -- the order of the float64
+// additions stays fixed.  Lane = dimension (and dimension + 32); the running sums of the current
+// cluster stay in registers and are added to the accumulator when the label changes.
+__device__ __forceinline__ void accumulate_rows(double *__restrict__ acc, const float *__restrict__ tile, int pitch,
+                                                const unsigned short *__restrict__ cstart,
+                                                const unsigned short *__restrict__ order, int K, int D,
+                                                int n_rows, int lane, int warp, int n_warps)
+{
+    const int per = (n_rows + n_warps - 1) / n_warps;
+    // first cluster of this warp / of the next warp: the first k with cstart[k] >= warp * per
+    auto first_cluster = [&](int row) {
+        if (row <= 0) return 0;
+        if (row >= n_rows) return K;
+        int best = K;
+        for (int k0 = 0; k0 < K; k0 += 32) {
+            const int k = k0 + lane;
+            const unsigned hit = __ballot_sync(0xffffffffu, k < K && (int)cstart[k] >= row);
+            if (hit) { best = k0 + __ffs(hit) - 1; break; }
+        }
+        return best;
+    };
+    const int ka = first_cluster(warp * per), kb = first_cluster((warp + 1) * per);
+    if (ka >= kb) return;
+    const int i0 = cstart[ka], i1 = cstart[kb];
+    const int da = lane, db = lane + 32;
+    const bool ina = da < D, inb = db < D;
+    int k = ka, k_end = cstart[ka + 1];
+    double sa = 0.0, sb = 0.0;
+    int members = 0;
+    for (int i = i0; i < i1; ++i) {
+        while (i >= k_end) {                              // label changes: flush the finished cluster (warp-uniform)
+            if (members) {
+                if (ina) acc[k * (D + 1) + da] += sa;
+                if (inb) acc[k * (D + 1) + db] += sb;
+                if (lane == 0) acc[k * (D + 1) + D] += (double)members;
+                sa = 0.0; sb = 0.0; members = 0;
+            }
+            ++k;
+            k_end = cstart[k + 1];
+        }
+        const float *row = tile + (int)order[i] * pitch;
+        if (ina) sa += (double)row[da];
+        if (inb) sb += (double)row[db];
+        ++members;
+    }
+    if (members) {
+        if (ina) acc[k * (D + 1) + da] += sa;
+        if (inb) acc[k * (D + 1) + db] += sb;
+        if (lane == 0) acc[k * (D + 1) + D] += (double)members;
+    }
+}
+
 // Byte offset of element (row r, 16-byte chunk c) of a K-major operand with `groups` groups of 8 rows.
 __device__ __forceinline__ uint32_t operand_offset(int r, int c, int groups) { return (uint32_t)(c * groups * 128 + (r >> 3) * 128 + (r & 7) * 16); }
 
@@ -198,6 +268,8 @@ kmeans_step_umma_kernel(const float *__restrict__ data, int64_t n_tiles, int D, 
         }
         *reinterpret_cast<float4 *>(smem + L.b + operand_offset(k, c, kUPad / 8)) = make_float4(v[0], v[1], v[2], v[3]);
     }
+    for (int i = tid; i < 2 * kUABytes / 16; i += kUThreads)           // operand A: the chunks past D stay zero for good
+        reinterpret_cast<float4 *>(smem + L.a)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (kAccumulate)
         for (int i = tid; i < K * (D + 1); i += kUThreads) acc[i] = 0.0;
     if (tid == 0) {
@@ -232,7 +304,7 @@ kmeans_step_umma_kernel(const float *__restrict__ data, int64_t n_tiles, int D, 
         if (lane == 0) {
             for (int64_t n = 0; n < n_cta; ++n) {
                 const int slot = (int)(n % kURing);
-                if (n >= kURing) mbar_wait_u(reinterpret_cast<unsigned long long *>(raw_empty) + slot, (unsigned)((n / kURing - 1) & 1));
+                if (n >= kURing) mbar_wait_backoff(reinterpret_cast<unsigned long long *>(raw_empty) + slot, (unsigned)((n / kURing - 1) & 1));
                 const int64_t tl = blockIdx.x + n * gridDim.x;
                 bulk_load_tile(raw + (size_t)slot * tile_floats, data + tl * tile_floats, tile_bytes,
                                reinterpret_cast<unsigned long long *>(raw_full) + slot);
@@ -257,25 +329,34 @@ kmeans_step_umma_kernel(const float *__restrict__ data, int64_t n_tiles, int D, 
             const int slot = (int)(n % kURing);
             const int64_t row0 = (blockIdx.x + n * gridDim.x) * (int64_t)kURows;
             const float *xt = raw + (size_t)slot * tile_floats;
-            mbar_wait_u(reinterpret_cast<unsigned long long *>(raw_full) + slot, (unsigned)((n / kURing) & 1));
+            // one thread waits for the tile (and later for the MMA); the others sleep at the group barrier
+            if (r == 0) mbar_wait_u(reinterpret_cast<unsigned long long *>(raw_full) + slot, (unsigned)((n / kURing) & 1));
             if (kAccumulate) zero_member_bits(bits, K, 4, r, kUGroup);
+            bar_sync(grp_bar, kUGroup);
 
             // ---- operand A: this thread's row, centred on the centroid mean, TF32, 16 bytes per step
             const float *x = xt + r * D;
             float nx2 = 0.f;
-#pragma unroll 4
-            for (int c = 0; c < kUPad / 4; ++c) {
+            const int c_full = D >> 2;
+#pragma unroll 2
+            for (int c = 0; c < c_full; ++c) {
                 const float4 m4 = *reinterpret_cast<const float4 *>(mean + 4 * c);
+                const float x0 = x[4 * c] - m4.x, x1 = x[4 * c + 1] - m4.y, x2 = x[4 * c + 2] - m4.z, x3 = x[4 * c + 3] - m4.w;
+                nx2 = fmaf(x0, x0, fmaf(x1, x1, fmaf(x2, x2, fmaf(x3, x3, nx2))));
+                *reinterpret_cast<uint4 *>(a_op + operand_offset(r, c, kURows / 8)) = make_uint4(to_tf32(x0), to_tf32(x1), to_tf32(x2), to_tf32(x3));
+            }
+            if (D & 3) {                                                           // the ragged last chunk
+                const float4 m4 = *reinterpret_cast<const float4 *>(mean + 4 * c_full);
                 const float mm[4] = {m4.x, m4.y, m4.z, m4.w};
-                float v[4];
+                uint32_t v[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int d = 4 * c + j;
-                    const float xv = d < D ? x[d] - mm[j] : 0.f;
-                    nx2 = fmaf(xv, xv, nx2);
-                    v[j] = __uint_as_float(to_tf32(xv));
-                }
-                *reinterpret_cast<float4 *>(a_op + operand_offset(r, c, kURows / 8)) = make_float4(v[0], v[1], v[2], v[3]);
+                for (int j = 0; j < 3; ++j)
+                    if (4 * c_full + j < D) {
+                        const float xv = x[4 * c_full + j] - mm[j];
+                        nx2 = fmaf(xv, xv, nx2);
+                        v[j] = to_tf32(xv);
+                    }
+                *reinterpret_cast<uint4 *>(a_op + operand_offset(r, c_full, kURows / 8)) = make_uint4(v[0], v[1], v[2], v[3]);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy writes -> visible to the tensor core
             tc_fence_before();
@@ -287,9 +368,10 @@ kmeans_step_umma_kernel(const float *__restrict__ data, int64_t n_tiles, int D, 
                     umma_tf32(tmem_acc, umma_desc(a_addr + ks * 2 * (kURows / 8) * 128, (kURows / 8) * 128, 128),
                               umma_desc(b_addr + ks * 2 * (kUPad / 8) * 128, (kUPad / 8) * 128, 128), ks > 0 ? 1u : 0u);
                 umma_commit(reinterpret_cast<unsigned long long *>(mma_done) + g);
+                mbar_wait_u(reinterpret_cast<unsigned long long *>(mma_done) + g, uses & 1u);
             }
-            mbar_wait_u(reinterpret_cast<unsigned long long *>(mma_done) + g, uses & 1u);
             ++uses;
+            bar_sync(grp_bar, kUGroup);
             tc_fence_after();
 
             // ---- stage A epilogue: the row's 64 ranking values, their minimum, the candidates
@@ -341,7 +423,7 @@ kmeans_step_umma_kernel(const float *__restrict__ data, int64_t n_tiles, int D, 
                 bar_sync(grp_bar, kUGroup);
                 // the accumulators are shared by the two groups: tiles are added in tile order
                 if (n >= 1) bar_sync(3 + (1 - g), 2 * kUGroup);
-                accumulate_tile(acc, xt, D, cstart, order, K, D, lane, wg, 4);
+                accumulate_rows(acc, xt, D, cstart, order, K, D, kURows, lane, wg, 4);
                 __threadfence_block();
                 bar_sync(grp_bar, kUGroup);
                 if (n + 1 < n_cta) bar_arrive(3 + g, 2 * kUGroup);

@@ -10,7 +10,9 @@ printed through `%.18g` of its float64 value (plyfile's `_write_txt`).
 
 Only what the labelled-PLY path needs is supported: scalar properties (list properties are
 rejected), any number of elements (non-vertex elements are carried through verbatim for
-binary files).  Parity with plyfile could not be diffed in this container.
+binary files).  plyfile itself is not available here; tests/test_ply_bytes.py pins the written
+bytes from the consumer's side instead (a restatement of the viewer's parser,
+Web_Viewer_Gaussians_Selection/gaussians_selection.js:464-511 and :579, and literal known answers).
 """
 from __future__ import annotations
 
@@ -102,10 +104,14 @@ def read_ply(path_or_file) -> PlyFile:
             if fmt == "ascii":
                 dt = np.dtype([(n, "<" + c) for n, c in props])
                 arr = np.empty(count, dt)
-                for i in range(count):
-                    vals = f.readline().split()
-                    for (n, c), v in zip(props, vals):
-                        arr[n][i] = float(v) if c[0] == "f" else int(float(v))
+                if count:
+                    # one vertex per line, every field a decimal number: NumPy's C text reader
+                    # parses the whole element at once (float64, the precision plyfile prints with)
+                    cols = np.loadtxt(f, dtype=np.float64, max_rows=count, ndmin=2)
+                    if cols.shape != (count, len(props)):
+                        raise ValueError(f"PLY element {name!r}: expected {count} x {len(props)} values, found {cols.shape}")
+                    for j, (n, c) in enumerate(props):
+                        arr[n] = cols[:, j] if c[0] == "f" else cols[:, j].astype(np.int64)
             else:
                 order = "<" if fmt == "binary_little_endian" else ">"
                 dt = np.dtype([(n, order + c) for n, c in props])
