@@ -49,6 +49,7 @@ SIGNATURES = {
     "gsl_lift_prepare": (_i32, [_vp, _i64, _vp, _i32, _vp, _sz, _vp]),
     "gsl_lift_sweep": (_i32, [_vp, _i64, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
     "gsl_lift_gather": (_i32, [_vp, _i64, _vp, _i32, _vp, _vp, _sz, _vp]),
+    "gsl_lift_gather_range": (_i32, [_vp, _i64, _vp, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
     "gsl_lift_majority": (_i32, [_i64, _i32, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
     "gsl_lift_merge": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp]),
     "gsl_lift_near": (_i32, [_vp, _i64, _vp, _i32, _vp, _dbl, _vp, _sz, _vp]),

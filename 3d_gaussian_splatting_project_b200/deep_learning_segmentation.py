@@ -236,7 +236,7 @@ class _Staged:
         self.h2d_bytes, self.views_as_int32, self.views_narrowed = h2d_bytes, views_as_int32, views_narrowed
 
 
-def _stage_pipelined(seg_maps, shapes, device, before_wait=None):
+def _stage_pipelined(seg_maps, shapes, device, before_wait=None, on_packed=None):
     """One-process staging of HOST (or device) maps, organised around the PCIe transfer, which is
     what such a call waits for (N2 of SURVEY 8f):
 
@@ -247,7 +247,9 @@ def _stage_pipelined(seg_maps, shapes, device, before_wait=None):
         device (gsl_tile_codes).
 
     The first uploads are enqueued before anything else happens on the host; `before_wait` (the
-    Gaussian ordering, which reads no maps) is called right after them.  Codes are label + 2
+    Gaussian ordering, which reads no maps) is called right after them, and `on_packed(v)` every
+    time the packed maps of views [0, v) have been enqueued on the main stream, so that the caller
+    can sweep them while later maps are still crossing the bus.  Codes are label + 2
     (label_min = -1, 254 codes); the caller checks the value range and re-stages when the labels do
     not fit that window."""
     import ctypes
@@ -306,6 +308,8 @@ def _stage_pipelined(seg_maps, shapes, device, before_wait=None):
             slot_free[ci % 2].record(main)
             if ci + 2 < n_dev:
                 n_px[ci + 2] = upload(ci + 2)            # refills the slot just packed
+            if on_packed is not None:
+                on_packed(v1, packed)
         # ---- chunks narrowed on the host, a few at a time, while the DMA engine is busy with the above
         host_mm = (ctypes.c_int * 2)(2**31 - 1, -2**31)
         if n_host:
@@ -350,6 +354,8 @@ def _stage_pipelined(seg_maps, shapes, device, before_wait=None):
                 for v, n in _runs(shapes, vb0, vb1):
                     check(L.gsl_tile_codes(codes.data_ptr() + int(starts[v] - starts[hv0]), n, shapes[v][1], shapes[v][0],
                                            packed.data_ptr() + int(pstarts[v]), main.cuda_stream))
+                if on_packed is not None:
+                    on_packed(vb1, packed)
             if t_narrow > 0:
                 _host_stage["px_per_s"] = px_narrow / t_narrow
                 # the other host work of this call; first calls also pay allocations, hence the cap
@@ -524,14 +530,28 @@ def lift_labels(positions, cameras, seg_maps, image_sizes=None, device=None, wan
             check(L.gsl_lift_prepare(pos.data_ptr(), N, views.ctypes.data, V, ws.data_ptr(), ws.numel(), main.cuda_stream))
         state.update(pos=pos, views=views, N=N, ws=ws)
 
-    def sweep(packed, lmin, ncls, best=None):
+    def sweep(packed, lmin, ncls, best=None, v_from=0):
+        """Gather views [v_from, V) (earlier ones were swept while the maps were uploading), then the majority."""
         labels = torch.empty(state["N"], dtype=torch.int32, device=device)
+        a = (state["pos"].data_ptr(), state["N"], state["views"].ctypes.data, V)
+        w = (state["ws"].data_ptr(), state["ws"].numel(), main.cuda_stream)
         with torch.cuda.device(device):
-            check(L.gsl_lift_sweep(state["pos"].data_ptr(), state["N"], state["views"].ctypes.data, V,
-                                   packed.data_ptr() if V else None, int(lmin), int(ncls), labels.data_ptr(),
-                                   best.data_ptr() if best is not None else None,
-                                   state["ws"].data_ptr(), state["ws"].numel(), main.cuda_stream))
+            check(L.gsl_lift_gather_range(*a, int(v_from), V, packed.data_ptr(), *w))
+            check(L.gsl_lift_majority(state["N"], V, int(lmin), int(ncls), labels.data_ptr(),
+                                      best.data_ptr() if best is not None else None, *w))
         return labels
+
+    swept = [0]
+
+    def sweep_resident(v_done, packed):
+        """Staging callback: views [0, v_done) are packed (enqueued on the main stream); sweep the
+        complete groups of 32 among them -- a sweep CTA takes two 16-view windows."""
+        target = v_done if v_done == V else v_done // 32 * 32
+        if target > swept[0]:
+            with torch.cuda.device(device):
+                check(L.gsl_lift_gather_range(state["pos"].data_ptr(), state["N"], state["views"].ctypes.data, V, swept[0], target,
+                                              packed.data_ptr(), state["ws"].data_ptr(), state["ws"].numel(), main.cuda_stream))
+            swept[0] = target
 
     if V == 0 or positions.shape[0] == 0:
         labels = np.full(positions.shape[0], -1, dtype=np.int32)
@@ -546,14 +566,14 @@ def lift_labels(positions, cameras, seg_maps, image_sizes=None, device=None, wan
     elif world > 1:
         st = _stage_sharded(seg_maps, shapes, device, dist, world, rank, before_wait=prepare)
     else:
-        st = _stage_pipelined(seg_maps, shapes, device, before_wait=prepare)
+        st = _stage_pipelined(seg_maps, shapes, device, before_wait=prepare, on_packed=sweep_resident)
     if st.lo < st.label_min or st.hi > st.label_min + st.n_classes - 1:
         if label_min is not None and n_classes is not None:
             raise ValueError(f"label map value outside [{label_min}, {label_min + n_classes})")
         wide = True
     if not wide:
         ncls = max(st.hi - st.label_min + 1, 1) if st.hi >= st.lo else 1      # fewer histogram rows per Gaussian
-        labels = sweep(st.packed, st.label_min, min(ncls, st.n_classes))
+        labels = sweep(st.packed, st.label_min, min(ncls, st.n_classes), v_from=swept[0])
     else:
         dense, uniq = _stage_wide(seg_maps, shapes, device)
         n_ids = int(uniq.numel())

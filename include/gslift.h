@@ -164,6 +164,11 @@ int gsl_lift_sweep(const float *pos, int64_t N, const GslView *views, int V,
  */
 int gsl_lift_gather(const float *pos, int64_t N, const GslView *views, int V,
                     const uint8_t *packed, void *ws, size_t ws_bytes, void *stream);
+/* gather for views [v_begin, v_end) only (v_begin a multiple of 16; v_end a multiple of 16 or V):
+ * lets a caller sweep the views whose packed maps are already resident while later maps are still
+ * crossing PCIe.  gsl_lift_gather == the range [0, V). */
+int gsl_lift_gather_range(const float *pos, int64_t N, const GslView *views, int V, int v_begin, int v_end,
+                          const uint8_t *packed, void *ws, size_t ws_bytes, void *stream);
 int gsl_lift_majority(int64_t N, int V, int label_min, int n_classes, int32_t *labels, uint32_t *best,
                       void *ws, size_t ws_bytes, void *stream);
 /* labels[i], best[i] = the pair with the larger key of (labels, best) and (labels_b, best_b). */

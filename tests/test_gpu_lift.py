@@ -368,3 +368,50 @@ def test_device_resident_maps_written_just_before_the_call(oracle):
         dev_maps = [(m * 1) for m in staged]               # produced asynchronously, right before the call
         got = dls.lift_labels(pos, cams, dev_maps)
         compare(got, want)
+
+
+_MGPU_LIFT_WORKER = r'''
+import os, sys, importlib
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+gs = importlib.import_module("3d_gaussian_splatting_project_b200")
+from oracle import oracle as orc
+sharding, dls, scene = gs.sharding, gs.deep_learning_segmentation, gs.scene
+rank, world, local = sharding.init_from_env("nccl")
+dev = torch.device("cuda", local)
+v, w, h, n = 70, 640, 360, 120_001
+cams = scene.lookat_cameras(v, width=w, height=h, seed=71)
+pos = scene.gaussian_cloud(n, 1.5, seed=72)
+maps = [scene.block_label_map(h, w, 8, -1, 149, 1000 + i) for i in range(v)]
+lo, hi = sharding.slice_bounds(n, rank, world)
+for rep in range(2):                                   # the second call reuses the symmetric-memory buffer
+    mine = dls.lift_labels(pos[lo:hi], cams, maps, device=dev)
+    whole = sharding.gather_labels(torch.from_numpy(mine).to(dev), n, rank, world)
+    if rank == 0:
+        want, _, _ = orc.lift_votes(pos, orc.make_views(cams, [(h, w)] * v), np.stack(maps))
+        got = whole.cpu().numpy()
+        assert np.array_equal(got, want), int((got != want).sum())
+    if os.environ.get("GSLIFT_STAGE_EXCHANGE") != "nccl":
+        assert dls.last_call_stats["h2d_bytes"] < 4 * w * h * (v // world + 1) + 12 * (hi - lo) + 64, dls.last_call_stats
+torch.cuda.synchronize(); dist.barrier(); dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs on one node")
+@pytest.mark.parametrize("exchange", ["symm", "nccl"])
+def test_sharded_staging_and_lifting_on_several_ranks(tmp_path, exchange):
+    """One process per GPU through lift_labels: every rank uploads and packs only its block of
+    views and pushes the packed chunks into all ranks' buffers over peer memory (or broadcasts them
+    with NCCL); each rank lifts its slice of the Gaussians; gathered labels == the oracle's."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "mgpu_lift_worker.py"
+    script.write_text(_MGPU_LIFT_WORKER)
+    n = min(torch.cuda.device_count(), 8)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", GSLIFT_STAGE_EXCHANGE=exchange)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+                          "--master-addr", "127.0.0.1", "--master-port", "29743", str(script), root],
+                         capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert out.stdout.count("ok") == n
