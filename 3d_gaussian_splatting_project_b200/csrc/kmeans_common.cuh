@@ -148,4 +148,59 @@ __device__ __forceinline__ void accumulate_tile(double *__restrict__ acc, const 
     }
 }
 
+// Per-cluster sums of one sorted tile, walking ROWS instead of clusters: with a few hundred rows and up to 64
+// clusters a cluster has a handful of members, so a loop per cluster is mostly overhead.  Warp w
+// takes the clusters whose first sorted row lies in [32 w, 32 w + 32): whole clusters, contiguous
+// sorted rows, about 32 of them, and no cluster is shared between warps -- the order of the float64
+// additions stays fixed.  Lane = dimension (and dimension + 32); the running sums of the current
+// cluster stay in registers and are added to the accumulator when the label changes.
+__device__ __forceinline__ void accumulate_rows(double *__restrict__ acc, const float *__restrict__ tile, int pitch,
+                                                const unsigned short *__restrict__ cstart,
+                                                const unsigned short *__restrict__ order, int K, int D,
+                                                int n_rows, int lane, int warp, int n_warps)
+{
+    const int per = (n_rows + n_warps - 1) / n_warps;
+    // first cluster of this warp / of the next warp: the first k with cstart[k] >= warp * per
+    auto first_cluster = [&](int row) {
+        if (row <= 0) return 0;
+        if (row >= n_rows) return K;
+        int best = K;
+        for (int k0 = 0; k0 < K; k0 += 32) {
+            const int k = k0 + lane;
+            const unsigned hit = __ballot_sync(0xffffffffu, k < K && (int)cstart[k] >= row);
+            if (hit) { best = k0 + __ffs(hit) - 1; break; }
+        }
+        return best;
+    };
+    const int ka = first_cluster(warp * per), kb = first_cluster((warp + 1) * per);
+    if (ka >= kb) return;
+    const int i0 = cstart[ka], i1 = cstart[kb];
+    const int da = lane, db = lane + 32;
+    const bool ina = da < D, inb = db < D;
+    int k = ka, k_end = cstart[ka + 1];
+    double sa = 0.0, sb = 0.0;
+    int members = 0;
+    for (int i = i0; i < i1; ++i) {
+        while (i >= k_end) {                              // label changes: flush the finished cluster (warp-uniform)
+            if (members) {
+                if (ina) acc[k * (D + 1) + da] += sa;
+                if (inb) acc[k * (D + 1) + db] += sb;
+                if (lane == 0) acc[k * (D + 1) + D] += (double)members;
+                sa = 0.0; sb = 0.0; members = 0;
+            }
+            ++k;
+            k_end = cstart[k + 1];
+        }
+        const float *row = tile + (int)order[i] * pitch;
+        if (ina) sa += (double)row[da];
+        if (inb) sb += (double)row[db];
+        ++members;
+    }
+    if (members) {
+        if (ina) acc[k * (D + 1) + da] += sa;
+        if (inb) acc[k * (D + 1) + db] += sb;
+        if (lane == 0) acc[k * (D + 1) + D] += (double)members;
+    }
+}
+
 }  // namespace gsl

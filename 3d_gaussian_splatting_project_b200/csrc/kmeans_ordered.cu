@@ -11,9 +11,12 @@
 //   ordered_start_kernel     exclusive scan of the totals -> segment starts
 //   ordered_scatter_kernel   stable scatter of row indices into per-cluster member lists
 //                            (warp match_any ranks keep ascending row order)
-//   ordered_chain_kernel     CTA per cluster: consumer warps (lane = dimension) add the member rows in
-//                            order out of a shared-memory ring that the producer warps fill, batches
-//                            handed over with mbarriers
+//   ordered_chain_kernel     CTA per (cluster, 32 dims): seven producer warps cp.async member rows
+//                            into a 4-deep shared-memory ring while warp 0 adds them in
+//                            order, lane = dimension.  (Round 2 tried one CTA per cluster with an
+//                            mbarrier-advanced ring, consumers never at a block barrier: 12.5 ms
+//                            against 4.5 ms for this kernel at 6 M x 59 -- two dependent DRAM round
+//                            trips per batch and warp, index then rows; reverted.)
 //   shift_kernel             ||new - old||_F
 //
 // This is the parity mode (single device).  The throughput mode is gsl_kmeans_step's float64
@@ -119,120 +122,111 @@ ordered_scatter_kernel(const int32_t *__restrict__ labels, int64_t N, int K,
     }
 }
 
-// One CTA of 512 threads per cluster.  The float32 sum of a cluster's members is ONE dependent
-// chain per dimension (4 cycles per add): nothing can shorten it, so everything else is arranged
-// never to make it wait.
-//   consumers  ceil(D / 32) warps, lane = dimension: they own the accumulators and add member rows
-//              strictly in index order, straight out of a ring of row batches in shared memory;
-//   producers  the other warps: warp p fetches batches p, p + P, ... -- 32 member indices in one
-//              coalesced load, then the 32 rows (every row a couple of coalesced 128-byte loads, all
-//              of them in flight before the first store), written into the batch's ring slot.
-// A batch is handed over with a pair of mbarriers (full / empty) per ring slot, so the consumers
-// never wait on a block barrier and a producer that is merely issuing loads never holds them up
-// (round 1 used __syncthreads per batch and 4-byte cp.async: 5.1 ms at 6 M x 59, K = 64, against a
-// chain floor of 1.5 ms for the largest cluster).
-constexpr int kChainThreads = 512;
-constexpr int kChainBatch = 32;        // rows per batch == rows a producer warp fetches at a time
-constexpr int kChainSlots = 16;        // batches in the ring (fewer when D > 96: the ring must fit shared memory)
+// grid (K, ceil(D/32)); lane = dimension d0 + lane.  Warp 0 is the consumer: it owns the K*D/32
+// float32 accumulators of this (cluster, dimension chunk) and adds member rows strictly in index
+// order.  Warps 1..7 are producers: they gather the member rows (128 bytes per row and chunk) with
+// cp.async straight into a ring of kChainRing shared-memory batches, three batches ahead of the
+// consumer, so the DRAM latency of the row gather is hidden behind the dependent add chain.
+constexpr int kChainRows = 7 * 32;     // rows per batch: 32 per producer warp
+constexpr int kChainRing = 4;
 
-__device__ __forceinline__ uint32_t chain_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void chain_bar_init(void *bar, unsigned count)
+__device__ __forceinline__ void cp_async_4(float *dst, const float *src)
 {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(chain_smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void chain_bar_arrive(void *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(chain_smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void chain_bar_wait(void *bar, unsigned parity)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "CW_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra CD_%=;\n\t"
-        "bra CW_%=;\n\t"
-        "CD_%=:\n\t"
-        "}" ::"r"(chain_smem_u32(bar)), "r"(parity) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
 
-__global__ void __launch_bounds__(kChainThreads, 1)
+__global__ void __launch_bounds__(kOrdThreads)
 ordered_chain_kernel(const float *__restrict__ data, int D, const int32_t *__restrict__ members,
                      const int64_t *__restrict__ start, const int64_t *__restrict__ total,
-                     const float *__restrict__ old_c, float *__restrict__ new_c, int n_slots)
+                     const float *__restrict__ old_c, float *__restrict__ new_c)
 {
-    extern __shared__ __align__(16) float ring[];          // [n_slots][kChainBatch][dp]
-    __shared__ unsigned long long full_bar[kChainSlots], empty_bar[kChainSlots];
-    const int k = blockIdx.x;
+    extern __shared__ float buf[];              // [kChainRing][kChainRows][32]
+    const int k = blockIdx.x, d = blockIdx.y * 32 + (threadIdx.x & 31);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int n_cons = (D + 31) / 32, n_prod = kChainThreads / 32 - n_cons;
-    const int dp = n_cons * 32;                            // floats per row slot
     const int64_t n = total[k], s0 = start[k];
-    if (n == 0) {                                          // km:126 else-branch: an empty cluster keeps its centroid
-        for (int d = threadIdx.x; d < D; d += kChainThreads) new_c[(size_t)k * D + d] = old_c[(size_t)k * D + d];
+    const bool live = d < D;
+    if (n == 0) {
+        if (w == 0 && live) new_c[(size_t)k * D + d] = old_c[(size_t)k * D + d];   // km:126 else-branch
         return;
     }
-    if (threadIdx.x < n_slots) {
-        chain_bar_init(&full_bar[threadIdx.x], 32);                        // the 32 lanes of the producer warp that filled it
-        chain_bar_init(&empty_bar[threadIdx.x], 32u * (unsigned)n_cons);   // every consumer lane
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    __syncthreads();
-    const int64_t n_batches = (n + kChainBatch - 1) / kChainBatch;
-    if (w < n_cons) {
-        // ===== consumer: dimension d, batches in order =====
-        const int d = w * 32 + lane;
-        float acc = -0.0f;              // (-0) + x == x for every x: same as starting from the first row
-        for (int64_t b = 0; b < n_batches; ++b) {
-            const int slot = (int)(b % n_slots);
-            chain_bar_wait(&full_bar[slot], (unsigned)((b / n_slots) & 1));
-            const int cnt = (int)min((int64_t)kChainBatch, n - b * kChainBatch);
-            const float *src = ring + ((size_t)slot * kChainBatch) * dp + d;
-            if (cnt == kChainBatch) {
-                float x[kChainBatch];
-#pragma unroll
-                for (int j = 0; j < kChainBatch; ++j) x[j] = src[j * dp];  // all loads first: the chain never waits for shared memory
-#pragma unroll
-                for (int j = 0; j < kChainBatch; ++j) acc = __fadd_rn(acc, x[j]);
-            } else {
-                for (int j = 0; j < cnt; ++j) acc = __fadd_rn(acc, src[j * dp]);
-            }
-            chain_bar_arrive(&empty_bar[slot]);
+    const int64_t n_batches = (n + kChainRows - 1) / kChainRows;
+    // producers: this warp's 32 rows of batch b.  The member indices of a batch are loaded one
+    // iteration before its copies are issued (load_idx -> issue): otherwise the latency of that
+    // load (~1 us) sits in front of every batch's cp.async and, through the barrier, in front of the
+    // consumer (profiles/r1/ncu_ordered_chain_r1.txt: the producers' first SHFL held 20 % of all samples).
+    auto load_idx = [&](int64_t b) -> int {
+        if (w > 0 && b < n_batches) {
+            const int64_t mi = b * kChainRows + (w - 1) * 32 + lane;
+            return mi < n ? __ldg(members + s0 + mi) : -1;
         }
-        if (d < D) new_c[(size_t)k * D + d] = (float)((double)acc / (double)n);
-    } else {
-        // ===== producer =====
-        const int p = w - n_cons;
-        for (int64_t b = p; b < n_batches; b += n_prod) {
-            const int slot = (int)(b % n_slots);
-            const int64_t use = b / n_slots;
-            const int64_t mi = b * kChainBatch + lane;
-            const int my_idx = mi < n ? __ldg(members + s0 + mi) : -1;     // before the wait: in flight while the slot drains
-            if (use > 0) chain_bar_wait(&empty_bar[slot], (unsigned)((use - 1) & 1));
-            float *dst = ring + ((size_t)slot * kChainBatch) * dp + lane;
-            // 8 rows at a time: all their loads are issued before the first store
-#pragma unroll 1
-            for (int j0 = 0; j0 < kChainBatch; j0 += 8) {
-                float v[8][8];
-                int idx[8];
+        return -1;
+    };
+    // per row: one broadcast shared load (the row index, parked there by the lane that fetched it),
+    // one 32 x 32 -> 64-bit multiply-add (the source address) and the copy itself -- the seven
+    // producer warps share the SM's issue slots with the consumer.  (Broadcasting the indices with
+    // shuffles compiled to a dozen instructions per row: the warp-uniform branch around them is not
+    // provably convergent, so every shuffle came with its own collective-sync scaffolding.)
+    __shared__ int idx_s[7 * 32];
+    const char *base = reinterpret_cast<const char *>(data + (live ? d : 0));
+    asm volatile("" : "+l"(base));                               // keep it in registers, do not re-derive it per row
+    const unsigned row_bytes = (unsigned)D * 4u;
+    const unsigned buf_s = (unsigned)__cvta_generic_to_shared(buf);
+    auto issue = [&](int64_t b, int idx) {
+        if (w > 0 && b < n_batches) {
+            int *mine = idx_s + (w - 1) * 32;
+            __syncwarp();                                        // the previous batch's reads of this warp's slots are done
+            mine[lane] = idx;
+            __syncwarp();
+            unsigned dst = buf_s + (((unsigned)(b % kChainRing) * kChainRows + (unsigned)(w - 1) * 32u) * 32u + (unsigned)lane) * 4u;
+            asm volatile("" : "+r"(dst));                        // one register plus an immediate per row
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    idx[j] = __shfl_sync(0xffffffffu, my_idx, j0 + j);
-                    const float *row = data + (size_t)(idx[j] < 0 ? 0 : idx[j]) * D;
+            for (int j0 = 0; j0 < 32; j0 += 8) {
+                int r[8];
 #pragma unroll
-                    for (int c = 0; c < 8; ++c)
-                        if (c < n_cons) v[j][c] = (idx[j] >= 0 && c * 32 + lane < D) ? __ldg(row + c * 32 + lane) : 0.f;
-                }
+                for (int j = 0; j < 8; ++j) r[j] = mine[j0 + j];
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-#pragma unroll
-                    for (int c = 0; c < 8; ++c)
-                        if (c < n_cons) dst[(size_t)(j0 + j) * dp + c * 32] = v[j][c];
+                    if (live && r[j] >= 0)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + (unsigned)(j0 + j) * 128u), "l"(base + (size_t)(unsigned)r[j] * row_bytes) : "memory");
             }
-            chain_bar_arrive(&full_bar[slot]);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    for (int p = 0; p < kChainRing - 1; ++p) issue(p, load_idx(p));
+    int idx_next = load_idx(kChainRing - 1);
+    float acc = -0.0f;              // (-0) + x == x for every x: same as starting from the first row
+    for (int64_t b = 0; b < n_batches; ++b) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(kChainRing - 2) : "memory");   // my part of batch b landed
+        __syncthreads();            // everyone's part landed; the consumer is done with batch b - 1
+        issue(b + kChainRing - 1, idx_next);    // refills the slot batch b - 1 occupied
+        idx_next = load_idx(b + kChainRing);    // in flight while the consumer adds batch b
+        if (w == 0 && live) {
+            const int cnt = (int)min((int64_t)kChainRows, n - b * kChainRows);
+            const float *src = buf + (size_t)(b % kChainRing) * kChainRows * 32 + lane;
+            // the adds are one dependent chain (4 cycles each); the shared loads of the NEXT 32
+            // values are issued before the 32 adds of the current ones, so the chain does not wait
+            // for shared memory inside a batch
+            int i = 0;
+            if (cnt >= 32) {
+                float x[32], y[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = src[j * 32];
+                for (; i + 64 <= cnt; i += 32) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) y[j] = src[(i + 32 + j) * 32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc = __fadd_rn(acc, x[j]);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) x[j] = y[j];
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc = __fadd_rn(acc, x[j]);
+                i += 32;
+            }
+            for (; i < cnt; ++i) acc = __fadd_rn(acc, src[i * 32]);
         }
     }
+    if (w == 0 && live) new_c[(size_t)k * D + d] = (float)((double)acc / (double)n);
 }
 
 __global__ void __launch_bounds__(256)
@@ -311,12 +305,10 @@ extern "C" int gsl_kmeans_update_ordered(const float *data, const int32_t *label
         ordered_scatter_kernel<<<n_tiles, kOrdThreads, sc_smem, st>>>(labels, N, K, tile_counts, start, members);
         GSL_LAUNCH_CHECK("ordered_scatter_kernel");
     }
-    const size_t batch_bytes = (size_t)kChainBatch * (size_t)((D + 31) / 32 * 32) * sizeof(float);
-    int n_slots = (int)((size_t)200 * 1024 / batch_bytes);
-    if (n_slots > kChainSlots) n_slots = kChainSlots;
-    const size_t ch_smem = (size_t)n_slots * batch_bytes;
+    const size_t ch_smem = (size_t)kChainRing * kChainRows * 32 * sizeof(float);
     GSL_CUDA_TRY(cudaFuncSetAttribute(ordered_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch_smem));
-    ordered_chain_kernel<<<(unsigned)K, kChainThreads, ch_smem, st>>>(data, D, members, start, total, old_centroids, new_centroids, n_slots);
+    dim3 grid((unsigned)K, (unsigned)((D + 31) / 32));
+    ordered_chain_kernel<<<grid, kOrdThreads, ch_smem, st>>>(data, D, members, start, total, old_centroids, new_centroids);
     GSL_LAUNCH_CHECK("ordered_chain_kernel");
     shift_kernel<<<1, 256, 0, st>>>(new_centroids, old_centroids, K * D, shift, bad_label);
     GSL_LAUNCH_CHECK("shift_kernel");

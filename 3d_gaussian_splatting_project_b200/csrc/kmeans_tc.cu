@@ -133,7 +133,7 @@ template <bool kAccumulate, bool kCheck>
 __global__ void __launch_bounds__(kTcThreads, 2)
 kmeans_step_tc_kernel(const float *__restrict__ data, int64_t N, int D, const float *__restrict__ centroids,
                       int K, int32_t *__restrict__ labels, double *__restrict__ partials,
-                      TcSmem L, int vec_ok, float eps, unsigned long long *__restrict__ check_out)
+                      TcSmem L, int vec_ok, float eps, unsigned long long *__restrict__ check_out, int row_walk)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     double *acc = reinterpret_cast<double *>(smem + L.acc);
@@ -285,7 +285,8 @@ kmeans_step_tc_kernel(const float *__restrict__ data, int64_t N, int D, const fl
             __syncthreads();
             tile_row_order(bits, cstart, order, mine, same, kTcThreads / 32, t, lane, warp);
             __syncthreads();
-            accumulate_tile(acc, tile, pitch, cstart, order, K, D, lane, warp, kTcThreads / 32);
+            if (row_walk) accumulate_rows(acc, tile, pitch, cstart, order, K, D, kTcRows, lane, warp, kTcThreads / 32);
+            else accumulate_tile(acc, tile, pitch, cstart, order, K, D, lane, warp, kTcThreads / 32);
         }
         __syncthreads();                                 // every reader of the tile is done
         const int64_t nxt = tl + gridDim.x;
@@ -317,7 +318,8 @@ static int launch_tc_t(const float *data, int64_t N, int D, const float *centroi
     GSL_CUDA_TRY(cudaFuncSetAttribute(kmeans_step_tc_kernel<kAcc, kCheck>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     const int vec_ok = (((uintptr_t)data & 15) == 0);        // 256 rows x D floats is always a multiple of 16 bytes
     const float eps = (float)((D + 12) * 5.9604644775390625e-08);
-    kmeans_step_tc_kernel<kAcc, kCheck><<<grid, kTcThreads, L.total, st>>>(data, N, D, centroids, K, labels, partials, L, vec_ok, eps, check_out);
+    const char *rw = getenv("GSLIFT_KMEANS_ROWWALK");        // experiments: per-cluster sums by walking sorted rows (1) or clusters (0)
+    kmeans_step_tc_kernel<kAcc, kCheck><<<grid, kTcThreads, L.total, st>>>(data, N, D, centroids, K, labels, partials, L, vec_ok, eps, check_out, rw && rw[0] == '1' ? 1 : 0);
     GSL_LAUNCH_CHECK("kmeans_step_tc_kernel");
     return GSL_OK;
 }
