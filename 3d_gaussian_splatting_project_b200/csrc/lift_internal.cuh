@@ -121,8 +121,9 @@ struct alignas(16) HotView {
     uint32_t addr_k;        // folded constant of the float-derived offset (lift.cu: fast_pair), modulo 2^32
     uint64_t map;           // byte offset of the view's packed map; the sweep's staged copy holds its address
     uint32_t cstrip_m16;    // 16 * crows_pad - 16 (coarse strips)
-    uint32_t caddr_k;       // folded constant of the float-derived coarse offset, modulo 2^32
-    uint64_t cmap;          // byte offset (staged copy: address) of the view's coarse table
+    uint32_t caddr_k;       // spare
+    uint64_t cmap;          // byte offset (staged copy: address) of the view's coarse table, minus the folded
+                            // constant of the float-derived cell offset (lift.cu: fast_pair2)
 };
 static_assert(sizeof(HotView) == 96, "HotView is six 16-byte words");
 constexpr int kHotWords = sizeof(HotView) / 16;
