@@ -26,15 +26,14 @@ constexpr int kWin = 16;               // views per window (staging unit of the 
 // operations on values the float32 screening has in registers anyway (lift.cu).
 //
 // Behind the strips of a map lies its COARSE table: one byte per 8 x 8-pixel cell (half a 128-byte
-// line), the cell's code if all 64 pixels carry the same code, kMixed otherwise.  The table has
-// 2 * strips_x cells per row and rows_pad / 8 rows and is itself stored in strips of 16 cells (rows
-// padded to a multiple of 8), so that one of ITS 128-byte lines is a block of 16 x 8 cells = 128 x
-// 64 pixels: a warp's 32 lookups fall into one or two lines instead of one line per cell row.
-//     offc = (CX >> 4) * (16 * crows_pad) + 16 * CY + (CX & 15) = CX + 16 CY + (CX >> 4) (16 crows_pad - 16)
+// line), the cell's code if all 64 pixels carry the same code, kMixed otherwise; coarse_w =
+// 2 * strips_x cells per row, rows_pad / 8 rows, row-major:  offc = CY * coarse_w + CX.
 // Label maps are piecewise constant, so most lookups are answered by this table, which is 64
-// times smaller than the map, and the tables of all views of a scene (11 MB at 300 x 1920 x 1080)
-// stay in L2.  A kMixed cell sends the lookup to the full-resolution strips.  Results are
-// identical by construction.
+// times smaller than the map: the 32 lookups of a warp fall into a few sectors, and the tables of
+// all views of a scene (10 MB at 300 x 1920 x 1080) stay in L2.  A kMixed cell sends the lookup
+// to the full-resolution strips.  Results are identical by construction.
+// (The table was also tried in strips of 16 cells -- a 128-byte line = 16 x 8 cells: 2.0 tags per
+// lookup, no change in kernel time, one more multiply-add per lookup; measured in round 2.)
 // ---------------------------------------------------------------------------------------
 constexpr uint32_t kMixed = 255u;      // coarse-table marker; label codes are 1..254 (GSL_MAX_CODES)
 __host__ __device__ inline uint32_t map_strips_x(int seg_w) { return (uint32_t)((seg_w + 15) >> 4) + 2u; }
@@ -43,11 +42,9 @@ __host__ __device__ inline int64_t map_fine_bytes(int seg_w, int seg_h)
 {
     return (int64_t)map_strips_x(seg_w) * (int64_t)map_rows_pad(seg_h) * 16;
 }
-__host__ __device__ inline uint32_t map_coarse_strips(int seg_w) { return (2u * map_strips_x(seg_w) + 15u) >> 4; }
-__host__ __device__ inline uint32_t map_coarse_rows_pad(int seg_h) { return (map_rows_pad(seg_h) / 8u + 7u) & ~7u; }
 __host__ __device__ inline int64_t map_coarse_bytes(int seg_w, int seg_h)
 {
-    return (int64_t)map_coarse_strips(seg_w) * (int64_t)map_coarse_rows_pad(seg_h) * 16;
+    return ((int64_t)(2u * map_strips_x(seg_w)) * (int64_t)(map_rows_pad(seg_h) / 8u) + 15) / 16 * 16;
 }
 inline int64_t packed_map_bytes(int seg_w, int seg_h)
 {
@@ -95,18 +92,13 @@ __device__ __forceinline__ void pack_coords(int64_t i, uint32_t strips_x, uint32
 __device__ __forceinline__ void store_packed_row(uint8_t *__restrict__ packed, int64_t map_bytes, int64_t fine_bytes, int64_t m,
                                                  uint32_t strips_x, uint32_t rows_pad, uint32_t strip, uint32_t row, uint4 w, bool live)
 {
-    (void)strips_x;
     uint32_t left, right;
     coarse_cells_of_line(w, threadIdx.x & 31u, left, right);
     if (!live) return;
     uint8_t *base = packed + m * map_bytes;
     reinterpret_cast<uint4 *>(base)[(int64_t)strip * rows_pad + row] = w;
-    if ((row & 7u) == 0u) {
-        // cells (2 strip, row / 8) and (2 strip + 1, row / 8) of the coarse strips: adjacent bytes
-        const uint32_t cx = 2u * strip, crows_pad = (rows_pad / 8u + 7u) & ~7u;
-        *reinterpret_cast<unsigned short *>(base + fine_bytes + (int64_t)(cx >> 4) * (16u * crows_pad) + 16u * (row >> 3) + (cx & 15u)) =
-            (unsigned short)(left | right << 8);
-    }
+    if ((row & 7u) == 0u)
+        *reinterpret_cast<unsigned short *>(base + fine_bytes + (int64_t)(row >> 3) * (2u * strips_x) + 2u * strip) = (unsigned short)(left | right << 8);
 }
 
 // Everything the float32 sweep reads per (Gaussian, view) pair: 96 bytes, 16-byte aligned, the
@@ -120,7 +112,7 @@ struct alignas(16) HotView {
     uint32_t strip_m16;     // 16 * rows_pad - 16
     uint32_t addr_k;        // folded constant of the float-derived offset (lift.cu: fast_pair), modulo 2^32
     uint64_t map;           // byte offset of the view's packed map; the sweep's staged copy holds its address
-    uint32_t cstrip_m16;    // 16 * crows_pad - 16 (coarse strips)
+    uint32_t coarse_w;      // cells per row of the coarse table
     uint32_t caddr_k;       // spare
     uint64_t cmap;          // byte offset (staged copy: address) of the view's coarse table, minus the folded
                             // constant of the float-derived cell offset (lift.cu: fast_pair2)

@@ -51,8 +51,7 @@ def packed_map_bytes(seg_h: int, seg_w: int) -> int:
     plus a ring of zero codes, followed by the coarse table of 8 x 8-pixel cells)."""
     strips_x = (int(seg_w) + 15) // 16 + 2
     rows_pad = ((int(seg_h) + 7) // 8 + 2) * 8
-    # one byte per 8 x 8-pixel cell, in strips of 16 cells with the rows padded to a multiple of 8
-    coarse = ((2 * strips_x + 15) // 16) * ((rows_pad // 8 + 7) // 8 * 8) * 16
+    coarse = (2 * strips_x * (rows_pad // 8) + 15) // 16 * 16        # one byte per 8 x 8-pixel cell
     return strips_x * rows_pad * 16 + coarse
 
 
