@@ -239,22 +239,34 @@ __device__ __forceinline__ void lin_range(const float4 pl, const float (&lo)[3],
 // evaluation (coefficients rounded once, four roundings per form: error < 1e-6 * mag) against
 // margins of 1e-5 * mag plus 1e-6 px, so "no" is only ever said with room to spare; NaN says yes.
 // cz_lo = a lower bound of cz over the box (same margin).
-__device__ __forceinline__ bool box_may_be_visible(const float4 *__restrict__ pl, const float (&lo)[3], const float (&hi)[3], float &cz_lo)
+__device__ __forceinline__ bool box_may_be_visible(const float4 *__restrict__ pl, const float (&lo)[3], const float (&hi)[3],
+                                                   float &cz_lo, bool &interior)
 {
     const float rel = 1e-5f, px = 1e-6f;
     float mn, mx, mag;
+    interior = false;
     lin_range(pl[0], lo, hi, mn, mx, mag);
     cz_lo = mn - (rel * mag + 1e-30f);
     if (mx < -(rel * mag + 1e-30f)) return false;                          // every point has z <= 0
     const float zpos = fmaxf(mx, 0.f) * px;
+    const float zin = fmaxf(cz_lo, 0.f);
+    // `interior`: every point of the box is in front of the camera and projects to
+    // -15 <= x <= width + 1, -7 <= y <= height + 1, i.e. at least half a pixel inside the ring of the
+    // packed maps, so the sweep's clamp of the ring coordinates cannot act.  With cz >= cz_lo > 0:
+    //   x >= -15  <=>  p1 + 15 cz >= 0  <=  min p1 + 15 cz_lo >= 0,   x <= width + 1  <=  max p2 - cz_lo <= 0
     lin_range(pl[1], lo, hi, mn, mx, mag);
     if (mx < -(zpos + rel * mag)) return false;                            // x < 0 everywhere
+    bool in = cz_lo > 0.f && mn + 15.f * zin >= zpos + rel * mag;
     lin_range(pl[2], lo, hi, mn, mx, mag);
     if (mn > zpos + rel * mag) return false;                               // x >= width everywhere
+    in = in && mx - zin <= -(zpos + rel * mag);
     lin_range(pl[3], lo, hi, mn, mx, mag);
     if (mx < -(zpos + rel * mag)) return false;                            // y < 0 everywhere
+    in = in && mn + 7.f * zin >= zpos + rel * mag;
     lin_range(pl[4], lo, hi, mn, mx, mag);
     if (mn > zpos + rel * mag) return false;                               // y >= height everywhere
+    in = in && mx - zin <= -(zpos + rel * mag);
+    interior = in;
     return true;
 }
 
@@ -262,8 +274,9 @@ __device__ __forceinline__ bool box_may_be_visible(const float4 *__restrict__ pl
 // the error bound of lift.cu (screen_pair) is evaluated once for the whole tile: with
 // a >= |X|+|Y|+|Z| over the box and cz >= cz_lo > 0,
 //     k_max = (g_rm a + g_tm) / cz_lo,   E = k_max (FXH + span) + 3.03 u span + c0,
-// every factor rounded up; 1/2 - E, rounded down to a multiple of 2^-17, is what a pair's offset
-// from the pixel centre is compared with.
+// every factor rounded up; 1/2 - E, rounded down to a multiple of 2^-16, is what a pair's offset
+// from the pixel centre is compared with; bit 0 of the verdict says the tile is `interior`
+// (box_may_be_visible), which lets the sweep skip the clamp of the ring coordinates.
 __global__ void __launch_bounds__(256)
 order_verdict_kernel(const float *__restrict__ box, int64_t n_tiles, const float4 *__restrict__ planes,
                      const ViewFacts *__restrict__ facts, int V, int v_pad, int cull, int exact_only,
@@ -282,7 +295,8 @@ order_verdict_kernel(const float *__restrict__ box, int64_t n_tiles, const float
         if (b[6] == 0.f) {                                                  // a non-finite member: never cull, never fast
             const float lo[3] = {b[0], b[1], b[2]}, hi[3] = {b[3], b[4], b[5]};
             float cz_lo;
-            const bool vis = box_may_be_visible(planes + (size_t)v * 5, lo, hi, cz_lo);
+            bool interior;
+            const bool vis = box_may_be_visible(planes + (size_t)v * 5, lo, hi, cz_lo, interior);
             if (!vis && cull) {
                 out = kVerdictCull;
             } else if (slow == kVerdictGeneral && (f.flags & kViewBorder) && cz_lo > 0.f) {
@@ -293,7 +307,8 @@ order_verdict_kernel(const float *__restrict__ box, int64_t n_tiles, const float
                 const float room = 0.5f - E;                                // exact or rounded to nearest: inside c0's 1e-6
                 if (room >= 0.25f && a < 1e15f) {                           // false for NaN
                     unsigned q = (unsigned)(room * 131072.f) - 1u;          // floor, minus one step for the rounding of `room`
-                    out = q > 65533u ? 65533u : q;
+                    q = q > 65533u ? 65533u : q;
+                    out = (q & ~1u) | (interior ? 1u : 0u);                 // bit 0: the ring clamp cannot act (room >= 1/4: q >= 2)
                 }
             }
         }
