@@ -503,7 +503,7 @@ def run_native(a):
             "value_incl_pack": a.gaussians * V / ((ms_per_step + pack_ms) * 1e-3),
             "kernels_ms": {"prepare (ordering + per-tile verdicts)": prepare_ms, "lift_gather_kernel": sweep_ms,
                            "lift_majority_kernel": major_ms,
-                           "note": "each phase timed alone; in the timed step the majority of one chunk of Gaussians runs on a helper stream while the next chunk is swept, so ms_per_step < the sum",
+                           "note": "each phase timed alone with CUDA events; the timed step runs the same three phases back to back on one stream",
                            "pack_labels_all_views_staging (once per scene, not in value)": pack_ms},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": ncu_traffic("lift_gather_kernel", world), "kernel": "lift_gather_kernel",
