@@ -148,6 +148,7 @@ struct OrderWs {
     size_t sheet, pos_sorted, perm, keys, keys_sorted, idx, sort_temp, sort_temp_bytes, stats, tilebox, verdict, views, facts, hot, planes, bytes;
 };
 
+void fill_view_planes(const GslView &w, float4 (&planes)[5]);
 OrderWs order_layout(int64_t N, int V);
 int order_gaussians(const float *pos, int64_t N, int V, bool sort, bool exact_only, unsigned char *base, const OrderWs &L, cudaStream_t st);
 

@@ -18,10 +18,13 @@
 //                         bounding box (outliers clamp to the border cells), key = 24-bit Morton
 //                         code; non-finite positions take the last key
 //   sort_cells            (key, row) pairs by key (lift_sort.cu)
-//   order_permute_kernel  pos_sorted[i] = pos[perm[i]]
-//   order_tilebox_kernel  bounding box (+ non-finite flag) of each run of 256 sorted Gaussians
-//   order_planes_kernel   per view, the five half-spaces of the visibility test as linear forms
+//   order_permute_kernel  pos_sorted[i] = pos[perm[i]], and the bounding box (+ non-finite flag)
+//                         of each run of 256 sorted Gaussians (a CTA is one run)
+//   fill_view_planes      (host) per view, the five half-spaces of the visibility test as linear
+//                         forms; uploaded with the other view tables
 //   order_verdict_kernel  16 bits per (tile, view): cull / fast with its bound / general / exact
+// Eight stream operations besides the sort's five: at 750 K Gaussians per rank (8 GPUs) the pass
+// is launch-bound, so the small kernels of round 1 (grid, tile boxes, planes) were folded away.
 // The order inside a cell follows the input order (the sort is stable), so the whole ordering is
 // deterministic.  (A 1024^3 grid with 30-bit keys was measured: one more sort pass, same gather time.)
 #include "common.cuh"
@@ -80,9 +83,9 @@ order_stats_kernel(const float *__restrict__ pos, int64_t N, unsigned long long 
     if (threadIdx.x < 6) {                       // one atomic per CTA and bound
         float v = redf[threadIdx.x][0];
         for (int w = 1; w < 8; ++w) v = threadIdx.x < 3 ? fminf(v, redf[threadIdx.x][w]) : fmaxf(v, redf[threadIdx.x][w]);
+        // minima are kept as the complement of their code: every slot starts at 0 and only grows
         unsigned *slot = reinterpret_cast<unsigned *>(stats + threadIdx.x);
-        if (threadIdx.x < 3) atomicMin(slot, enc_f32(v));
-        else atomicMax(slot, enc_f32(v));
+        atomicMax(slot, threadIdx.x < 3 ? ~enc_f32(v) : enc_f32(v));
     } else if (threadIdx.x >= 32 && threadIdx.x < 39) {
         const int j = threadIdx.x - 32;
         double v = 0.0;
@@ -92,15 +95,13 @@ order_stats_kernel(const float *__restrict__ pos, int64_t N, unsigned long long 
 }
 
 // Grid of the ordering: per axis [max(min, mean - 4 sigma), min(max, mean + 4 sigma)] in 256 cells.
-// Only the quality of the ordering depends on it, never a result.
-__global__ void order_grid_kernel(unsigned long long *__restrict__ stats)
+// Only the quality of the ordering depends on it, never a result.  Every CTA of the key kernel
+// derives it from the statistics itself (three threads, a few float64 operations).
+__device__ __forceinline__ void order_grid_axis(const unsigned long long *__restrict__ stats, int a, float &lo_out, float &inv_out)
 {
-    const int a = threadIdx.x;
-    if (a >= 3) return;
     const double *d = reinterpret_cast<const double *>(stats);
-    float *grid = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(stats) + 128);
     const double n = d[12];
-    float lo = dec_f32((unsigned)stats[a]), hi = dec_f32((unsigned)stats[3 + a]);
+    float lo = dec_f32(~(unsigned)stats[a]), hi = dec_f32((unsigned)stats[3 + a]);
     if (n > 0.0) {
         const double mean = d[6 + a] / n;
         const double var = fmax(d[9 + a] / n - mean * mean, 0.0);
@@ -109,8 +110,8 @@ __global__ void order_grid_kernel(unsigned long long *__restrict__ stats)
         if (mean + 4.0 * sd < (double)hi) hi = (float)(mean + 4.0 * sd);
     }
     const float ext = hi - lo;
-    grid[a] = lo;
-    grid[3 + a] = (ext > 0.f && ext < INFINITY) ? 256.f / ext : 0.f;
+    lo_out = lo;
+    inv_out = (ext > 0.f && ext < INFINITY) ? 256.f / ext : 0.f;
 }
 
 __device__ __forceinline__ unsigned spread8(unsigned v)      // 8 bits -> every third bit
@@ -126,7 +127,9 @@ __global__ void __launch_bounds__(256)
 order_key_kernel(const float *__restrict__ pos, int64_t N, const unsigned long long *__restrict__ stats,
                  uint32_t *__restrict__ keys, int32_t *__restrict__ idx)
 {
-    const float *grid = reinterpret_cast<const float *>(reinterpret_cast<const unsigned char *>(stats) + 128);
+    __shared__ float grid[6];
+    if (threadIdx.x < 3) order_grid_axis(stats, threadIdx.x, grid[threadIdx.x], grid[3 + threadIdx.x]);
+    __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     unsigned q[3];
@@ -149,33 +152,24 @@ order_iota_kernel(int32_t *__restrict__ perm, int64_t N)
     if (i < N) perm[i] = (int32_t)i;
 }
 
+// pos_sorted[i] = pos[perm[i]] as float4 (one 16-byte load per Gaussian in the sweep), and, since a
+// CTA is exactly one tile of kTile sorted Gaussians, the tile's box = {lo xyz, hi xyz, nonfinite, 0}.
+static_assert(kTile == 256, "order_permute_kernel: one CTA of 256 threads per tile");
 __global__ void __launch_bounds__(256)
-order_permute_kernel(const float *__restrict__ pos, int64_t N, const int32_t *__restrict__ perm, float4 *__restrict__ pos_sorted)
+order_permute_kernel(const float *__restrict__ pos, int64_t N, const int32_t *__restrict__ perm, float4 *__restrict__ pos_sorted,
+                     float *__restrict__ box)
 {
+    __shared__ float red[8][8];
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    const int64_t s = perm[i];
-    pos_sorted[i] = make_float4(pos[3 * s + 0], pos[3 * s + 1], pos[3 * s + 2], 0.f);     // one 16-byte load per Gaussian in the sweep
-}
-
-// One warp per tile of kTile sorted Gaussians: box[tile] = {lo xyz, hi xyz, nonfinite, 0}.
-__global__ void __launch_bounds__(256)
-order_tilebox_kernel(const float4 *__restrict__ pos_sorted, int64_t N, int64_t n_tiles, float *__restrict__ box)
-{
-    const int64_t tile = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (tile >= n_tiles) return;
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
     int bad = 0;
-    for (int r = lane; r < kTile; r += 32) {
-        const int64_t g = tile * kTile + r;
-        if (g >= N) break;
-        const float4 p4 = pos_sorted[g];
-        const float pv[3] = {p4.x, p4.y, p4.z};
+    if (i < N) {
+        const int64_t s = perm[i];
+        const float pv[3] = {pos[3 * s + 0], pos[3 * s + 1], pos[3 * s + 2]};
+        pos_sorted[i] = make_float4(pv[0], pv[1], pv[2], 0.f);
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            const float v = pv[a];
-            if (fabsf(v) < INFINITY) { lo[a] = fminf(lo[a], v); hi[a] = fmaxf(hi[a], v); } else bad = 1;
+            if (fabsf(pv[a]) < INFINITY) { lo[a] = pv[a]; hi[a] = pv[a]; } else bad = 1;
         }
     }
 #pragma unroll
@@ -185,10 +179,19 @@ order_tilebox_kernel(const float4 *__restrict__ pos_sorted, int64_t N, int64_t n
             hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
         }
     bad = __any_sync(0xffffffffu, bad);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) {
-        float *b = box + tile * 8;
-        b[0] = lo[0]; b[1] = lo[1]; b[2] = lo[2]; b[3] = hi[0]; b[4] = hi[1]; b[5] = hi[2];
-        b[6] = bad ? 1.f : 0.f; b[7] = 0.f;
+        red[warp][0] = lo[0]; red[warp][1] = lo[1]; red[warp][2] = lo[2];
+        red[warp][3] = hi[0]; red[warp][4] = hi[1]; red[warp][5] = hi[2];
+        red[warp][6] = bad ? 1.f : 0.f;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        const int c = threadIdx.x;
+        float v = c == 7 ? 0.f : red[0][c];
+        if (c < 7)
+            for (int w = 1; w < 8; ++w) v = c < 3 ? fminf(v, red[w][c]) : fmaxf(v, red[w][c]);     // the flag is a max too
+        box[(int64_t)blockIdx.x * 8 + c] = v;
     }
 }
 
@@ -201,23 +204,19 @@ order_tilebox_kernel(const float4 *__restrict__ pos_sorted, int64_t N, int64_t n
 //   p4  fy*cy + (half_h - height)*cz         y <  height <=>  p4 <  0
 // planes[v][p] = {a0, a1, a2, c}.  A view with a non-finite parameter gets NaN planes, which
 // never cull.
-__global__ void __launch_bounds__(128)
-order_planes_kernel(const GslView *__restrict__ views, int V, float4 *__restrict__ planes)
+// (host side: the planes travel with the other view tables in the one upload of gsl_lift_prepare)
+void fill_view_planes(const GslView &w, float4 (&planes)[5])
 {
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= V) return;
-    const GslView w = views[v];
     const double kx[5] = {0.0, w.fx, w.fx, 0.0, 0.0};
     const double ky[5] = {0.0, 0.0, 0.0, w.fy, w.fy};
     const double kz[5] = {1.0, w.half_w, w.half_w - w.width, w.half_h, w.half_h - w.height};
-#pragma unroll
     for (int p = 0; p < 5; ++p) {
         float4 o;
         o.x = (float)(kx[p] * w.R[0] + ky[p] * w.R[3] + kz[p] * w.R[6]);
         o.y = (float)(kx[p] * w.R[1] + ky[p] * w.R[4] + kz[p] * w.R[7]);
         o.z = (float)(kx[p] * w.R[2] + ky[p] * w.R[5] + kz[p] * w.R[8]);
         o.w = (float)(kx[p] * w.t[0] + ky[p] * w.t[1] + kz[p] * w.t[2]);
-        planes[v * 5 + p] = o;
+        planes[p] = o;
     }
 }
 
@@ -356,7 +355,6 @@ int order_gaussians(const float *pos, int64_t N, int V, bool sort, bool exact_on
     unsigned long long *stats = reinterpret_cast<unsigned long long *>(base + L.stats);
     float *tilebox = reinterpret_cast<float *>(base + L.tilebox);
     uint16_t *verdict = reinterpret_cast<uint16_t *>(base + L.verdict);
-    GslView *d_views = reinterpret_cast<GslView *>(base + L.views);
     const ViewFacts *d_facts = reinterpret_cast<const ViewFacts *>(base + L.facts);
     float4 *planes = reinterpret_cast<float4 *>(base + L.planes);
     const int64_t n_tiles = (N + kTile - 1) / kTile;
@@ -364,15 +362,12 @@ int order_gaussians(const float *pos, int64_t N, int V, bool sort, bool exact_on
 
     const unsigned rows_grid = (unsigned)((N + 255) / 256);
     if (sort) {
-        GSL_CUDA_TRY(cudaMemsetAsync(stats, 0xff, 3 * 8, st));
-        GSL_CUDA_TRY(cudaMemsetAsync(stats + 3, 0x00, kStatsBytes - 3 * 8, st));
+        GSL_CUDA_TRY(cudaMemsetAsync(stats, 0x00, kStatsBytes, st));
         int64_t blocks = (N + 256 * 8 - 1) / (256 * 8);
         const int64_t cap = (int64_t)sm_count() * 8;
         if (blocks > cap) blocks = cap;
         order_stats_kernel<<<(unsigned)blocks, 256, 0, st>>>(pos, N, stats);
         GSL_LAUNCH_CHECK("order_stats_kernel");
-        order_grid_kernel<<<1, 32, 0, st>>>(stats);
-        GSL_LAUNCH_CHECK("order_grid_kernel");
         order_key_kernel<<<rows_grid, 256, 0, st>>>(pos, N, stats, keys, idx);
         GSL_LAUNCH_CHECK("order_key_kernel");
         if (int rc = sort_cells(keys, keys_sorted, idx, perm, N, base + L.sort_temp, L.sort_temp_bytes, st)) return rc;
@@ -380,12 +375,8 @@ int order_gaussians(const float *pos, int64_t N, int V, bool sort, bool exact_on
         order_iota_kernel<<<rows_grid, 256, 0, st>>>(perm, N);
         GSL_LAUNCH_CHECK("order_iota_kernel");
     }
-    order_permute_kernel<<<rows_grid, 256, 0, st>>>(pos, N, perm, pos_sorted);
+    order_permute_kernel<<<rows_grid, 256, 0, st>>>(pos, N, perm, pos_sorted, tilebox);       // rows_grid == n_tiles
     GSL_LAUNCH_CHECK("order_permute_kernel");
-    order_tilebox_kernel<<<(unsigned)((n_tiles + 7) / 8), 256, 0, st>>>(pos_sorted, N, n_tiles, tilebox);
-    GSL_LAUNCH_CHECK("order_tilebox_kernel");
-    order_planes_kernel<<<(V + 127) / 128, 128, 0, st>>>(d_views, V, planes);
-    GSL_LAUNCH_CHECK("order_planes_kernel");
     const int64_t threads = n_tiles * (int64_t)v_pad;
     order_verdict_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(tilebox, n_tiles, planes, d_facts, V, v_pad, sort ? 1 : 0, exact_only ? 1 : 0, verdict);
     GSL_LAUNCH_CHECK("order_verdict_kernel");

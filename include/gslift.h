@@ -160,7 +160,9 @@ int gsl_lift_sweep(const float *pos, int64_t N, const GslView *views, int V,
 /*
  * The two kernels of gsl_lift_sweep, separately callable (benchmarks time them one by one):
  * gather fills the vote sheet in `ws` (one uint8 code per (Gaussian, view), 4 views to a word),
- * majority reduces it to labels.
+ * majority reduces it to labels.  `views` must be the host array gsl_lift_prepare was given: the
+ * float32 constants of the swept views travel to the kernel as launch parameters, with the map
+ * addresses resolved against `packed`.
  */
 int gsl_lift_gather(const float *pos, int64_t N, const GslView *views, int V,
                     const uint8_t *packed, void *ws, size_t ws_bytes, void *stream);
