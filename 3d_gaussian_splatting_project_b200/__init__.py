@@ -13,10 +13,11 @@ Modules
     plyio                        PLY reader / writer (plyfile stand-in)
     scene                        synthetic scenes for tests and benchmarks
     sharding                     one-process-per-GPU helpers (Gaussian slices, NCCL)
+    viewer                       the viewer worker's depth sort and click hit test (gaussians_selection.js)
 """
 from importlib import import_module as _imp
 
-__all__ = ["deep_learning_segmentation", "k_means", "ops", "plyio", "scene", "sharding"]
+__all__ = ["deep_learning_segmentation", "k_means", "ops", "plyio", "scene", "sharding", "viewer"]
 
 
 def __getattr__(name):

@@ -9,7 +9,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgslift.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # Mirrors `GslView` in include/gslift.h.
 VIEW_DTYPE = np.dtype(
@@ -64,6 +64,10 @@ SIGNATURES = {
     "gsl_kmeans_screen_selftest": (_i32, [_vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp]),
     "gsl_ply_format_ascii": (_i64, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _i64, _i32]),
     "gsl_recolor": (_i32, [_vp, _i64, _vp, _vp, _vp]),
+    "gsl_viewer_sort_workspace_bytes": (_sz, [_i64]),
+    "gsl_viewer_depth_sort": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "gsl_viewer_hit_workspace_bytes": (_sz, []),
+    "gsl_viewer_hit_test": (_i32, [_vp, _vp, _i64, _i32, _vp, _dbl, _dbl, _dbl, _dbl, _i32, _vp, _vp, _vp, _sz, _vp]),
 }
 
 

@@ -1,0 +1,207 @@
+// Stable least-significant-digit radix sort of (uint32 key, uint32 payload) pairs, hand written
+// for sm_100a (no library).  One pass = histogram kernel + scan kernel + scatter kernel:
+//
+//   tile     = THREADS x ITEMS consecutive pairs; warp w of the tile owns a contiguous run of
+//              32 x ITEMS pairs and walks it in rounds of 32 consecutive pairs (lane = pair), so
+//              loads are fully coalesced and the order inside a tile is (warp, round, lane).
+//   ranking  = in a round, __match_any_sync groups the lanes holding the same digit; a lane's
+//              rank is the per-warp running count of its digit plus the number of lower lanes
+//              of its group -- no atomics, and the rank order is the input order (stability).
+//   bases    = hist[digit][tile] scanned in that (digit-major) order by one CTA.
+//
+// Used by the viewer-side depth sort (viewer.cu: 17-bit bucket keys, two 9-bit passes) and by
+// the k-nearest-neighbour grid of region_growing.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace gsl {
+namespace radix {
+
+constexpr int kThreads = 512;
+constexpr int kItems = 16;
+constexpr int kTile = kThreads * kItems;      // 8192 pairs per tile
+constexpr int kWarps = kThreads / 32;
+
+inline int n_tiles(int64_t N) { return (int)((N + kTile - 1) / kTile); }
+// uint32 words of histogram scratch one pass of `bits` bits needs.
+inline size_t hist_words(int64_t N, int bits) { return ((size_t)n_tiles(N) << bits) + 1; }
+
+__device__ __forceinline__ unsigned lanemask_lt()
+{
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// Per-warp digit counts of the tile's rounds; on return cnt[warp][d] holds the warp's total of
+// digit d and rank[r] the rank of the lane's pair of round r among the warp's pairs of that digit.
+template <int BITS>
+__device__ __forceinline__ void rank_warp_run(const uint32_t *__restrict__ keys, int64_t N, int64_t warp_begin,
+                                              int shift, uint32_t *cnt_warp, uint32_t (&key)[kItems],
+                                              uint32_t (&rank)[kItems])
+{
+    constexpr uint32_t DIG = 1u << BITS;
+    const unsigned lane = threadIdx.x & 31u, lt = lanemask_lt();
+#pragma unroll
+    for (int r = 0; r < kItems; ++r) {
+        const int64_t i = warp_begin + r * 32 + lane;
+        const bool valid = i < N;
+        const unsigned act = __ballot_sync(0xffffffffu, valid);
+        key[r] = 0;
+        rank[r] = 0;
+        if (valid) {
+            key[r] = keys[i];
+            const uint32_t d = (key[r] >> shift) & (DIG - 1u);
+            const unsigned peers = __match_any_sync(act, d);
+            const uint32_t pre = cnt_warp[d];
+            __syncwarp(act);
+            if ((peers & lt) == 0) cnt_warp[d] = pre + __popc(peers);
+            __syncwarp(act);
+            rank[r] = pre + __popc(peers & lt);
+        }
+    }
+}
+
+template <int BITS>
+__global__ void __launch_bounds__(kThreads) histogram_kernel(const uint32_t *__restrict__ keys, int64_t N, int shift,
+                                                             uint32_t *__restrict__ hist, int tiles)
+{
+    constexpr int DIG = 1 << BITS;
+    __shared__ uint32_t cnt[DIG];
+    for (int d = threadIdx.x; d < DIG; d += kThreads) cnt[d] = 0;
+    __syncthreads();
+    const int tile = blockIdx.x;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, lt = lanemask_lt();
+    const int64_t warp_begin = (int64_t)tile * kTile + (int64_t)warp * 32 * kItems;
+#pragma unroll 4
+    for (int r = 0; r < kItems; ++r) {
+        const int64_t i = warp_begin + r * 32 + lane;
+        const bool valid = i < N;
+        const unsigned act = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            const uint32_t d = (keys[i] >> shift) & (uint32_t)(DIG - 1);
+            const unsigned peers = __match_any_sync(act, d);
+            if ((peers & lt) == 0) atomicAdd(&cnt[d], (uint32_t)__popc(peers));
+        }
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < DIG; d += kThreads) hist[(size_t)d * tiles + tile] = cnt[d];
+}
+
+// Exclusive scan of n words in place by ONE CTA of 1024 threads (n is a few hundred thousand).
+__global__ void __launch_bounds__(1024) scan_kernel(uint32_t *__restrict__ v, int64_t n)
+{
+    __shared__ uint32_t warp_sum[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    // chunks of 1024 x 4 words, lane-contiguous 16-byte pieces would need alignment of n; plain
+    // coalesced words are enough for a table this small
+    for (int64_t base = 0; base < n; base += 1024 * 4) {
+        uint32_t x[4], s = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t i = base + (int64_t)threadIdx.x * 4 + j;
+            x[j] = i < n ? v[i] : 0u;
+            s += x[j];
+        }
+        uint32_t inc = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (unsigned)o) inc += t;
+        }
+        if (lane == 31) warp_sum[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = warp_sum[lane], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= (unsigned)o) wi += t;
+            }
+            warp_sum[lane] = wi - w;      // exclusive over warps
+        }
+        __syncthreads();
+        uint32_t run = carry + warp_sum[warp] + (inc - s);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t i = base + (int64_t)threadIdx.x * 4 + j;
+            if (i < n) v[i] = run;
+            run += x[j];
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = run;
+        __syncthreads();
+    }
+}
+
+// keys_out / pay_out may be NULL (not needed after the last pass / keys-only).  pay_in == NULL
+// means the payload is the pair's own position (first pass of an index sort).  A pair whose FULL
+// key equals drop_key gets `drop_payload` instead of its payload (viewer.cu: the typed-array
+// out-of-range quirk of the reference's counting sort); pass 0xffffffff to disable.
+template <int BITS>
+__global__ void __launch_bounds__(kThreads) scatter_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ pay_in,
+                                                           uint32_t *__restrict__ keys_out, uint32_t *__restrict__ pay_out,
+                                                           int64_t N, int shift, const uint32_t *__restrict__ base, int tiles,
+                                                           uint32_t drop_key, uint32_t drop_payload)
+{
+    constexpr int DIG = 1 << BITS;
+    __shared__ uint32_t cnt[kWarps][DIG];
+    for (int d = threadIdx.x; d < kWarps * DIG; d += kThreads) (&cnt[0][0])[d] = 0;
+    __syncthreads();
+    const int tile = blockIdx.x;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const int64_t warp_begin = (int64_t)tile * kTile + (int64_t)warp * 32 * kItems;
+    uint32_t key[kItems], rank[kItems];
+    rank_warp_run<BITS>(keys, N, warp_begin, shift, cnt[warp], key, rank);
+    __syncthreads();
+    for (int d = threadIdx.x; d < DIG; d += kThreads) {
+        uint32_t run = base[(size_t)d * tiles + tile];
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            const uint32_t c = cnt[w][d];
+            cnt[w][d] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kItems; ++r) {
+        const int64_t i = warp_begin + r * 32 + lane;
+        if (i < N) {
+            const uint32_t d = (key[r] >> shift) & (uint32_t)(DIG - 1);
+            const uint32_t at = cnt[warp][d] + rank[r];
+            if (keys_out) keys_out[at] = key[r];
+            if (pay_out) {
+                uint32_t p = pay_in ? pay_in[i] : (uint32_t)i;
+                if (key[r] == drop_key) p = drop_payload;
+                pay_out[at] = p;
+            }
+        }
+    }
+}
+
+// One stable pass on `st`.  hist: hist_words(N, BITS) words of scratch.
+template <int BITS>
+inline int pass(const uint32_t *keys, const uint32_t *pay_in, uint32_t *keys_out, uint32_t *pay_out, int64_t N,
+                int shift, uint32_t *hist, uint32_t drop_key, uint32_t drop_payload, cudaStream_t st)
+{
+    if (N <= 0) return GSL_OK;
+    const int tiles = n_tiles(N);
+    histogram_kernel<BITS><<<tiles, kThreads, 0, st>>>(keys, N, shift, hist, tiles);
+    GSL_LAUNCH_CHECK("radix::histogram_kernel");
+    scan_kernel<<<1, 1024, 0, st>>>(hist, (int64_t)tiles << BITS);
+    GSL_LAUNCH_CHECK("radix::scan_kernel");
+    scatter_kernel<BITS><<<tiles, kThreads, 0, st>>>(keys, pay_in, keys_out, pay_out, N, shift, hist, tiles, drop_key,
+                                                     drop_payload);
+    GSL_LAUNCH_CHECK("radix::scatter_kernel");
+    return GSL_OK;
+}
+
+}  // namespace radix
+}  // namespace gsl

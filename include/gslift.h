@@ -6,6 +6,8 @@
  * reference lines it replaces (paths relative to the reference root):
  *
  *   dls = deep_learning_segmentation.py      km = 3D_clustering/k_means.py
+ *   gs  = Web_Viewer_Gaussians_Selection/gaussians_selection.js
+ *   rg  = 3D_clustering/region_growing.py
  *
  * Conventions
  *   - plain C types only; every pointer is a DEVICE pointer owned by the caller unless the
@@ -30,7 +32,7 @@
 extern "C" {
 #endif
 
-#define GSL_ABI_VERSION 3
+#define GSL_ABI_VERSION 4
 
 #define GSL_OK        0
 #define GSL_EINVAL   -1   /* bad argument (NULL pointer, negative size, V/K/D out of range) */
@@ -277,6 +279,43 @@ int gsl_recolor(const int32_t *labels, int64_t N, const float *palette, float *c
 int64_t gsl_ply_format_ascii(const void *records, int64_t n_rows, int record_size, int n_fields,
                              const int *types, const int *offsets, char *out, int64_t out_cap,
                              int n_threads);
+
+/*
+ * Viewer-side consumers of the labels: the per-Gaussian loops the
+ * WebGL viewer's worker runs on every camera move and click.  JavaScript numbers are float64 and
+ * `| 0` is ToInt32; both entry points reproduce that arithmetic in the reference's order.
+ *   pos      float32, Gaussian i at pos + i * stride (stride in floats: 8 for the viewer's 32-byte
+ *            rows gs:237, 3 for gaussians['position'])
+ *
+ * gsl_viewer_depth_sort -- runSort (gs:417-462) without its early-out (gs:421-425, the caller's
+ * business): depth_i = ((vp[2]*x + vp[6]*y + vp[10]*z) * 4096) | 0, bucket_i = ((depth_i - min) *
+ * (65536 / (max - min))) | 0, depth_index = Gaussian indices in a STABLE order of increasing bucket
+ * (the counting sort of gs:449-457).  Gaussians whose bucket evaluates to 65536 fall off the end of
+ * the reference's 65536-entry typed arrays: they are absent from depthIndex and the tail of
+ * depthIndex keeps its initial zeros -- reproduced here.
+ *   view_proj    HOST float64 [16], the message the worker receives (gs:626); entries 2, 6, 10 are read
+ *   depth_index  uint32 [N] out (Uint32Array, gs:453)
+ */
+size_t gsl_viewer_sort_workspace_bytes(int64_t N);
+int gsl_viewer_depth_sort(const float *pos, int64_t N, int stride, const double *view_proj,
+                          uint32_t *depth_index, void *ws, size_t ws_bytes, void *stream);
+
+/*
+ * gsl_viewer_hit_test -- performHitTesting (gs:361-395): project every Gaussian with the combined
+ * matrix (gs:398-405; skipped when w <= 0), screen = (ndc + 1) * 0.5 * viewport, dist =
+ * Math.hypot(screen - click) (V8's algorithm), and among those with dist < 10 the one with the
+ * smallest (dist, depth), the lowest index winning a full tie, exactly as the sequential scan does
+ * (including its behaviour on a NaN depth).
+ *   matrix        HOST float64 [16] = multiply4(projectionMatrix, viewMatrix) (gs:110-123, :364)
+ *   labels        int32 [N] (labelData, gs:241)
+ *   no_selection  value written when nothing is within 10 px (NO_SELECTION = -999999, gs:6)
+ *   label_out     int32 device scalar out (may be NULL);  index_out  int64 device scalar out (may be
+ *                 NULL): index of the selected Gaussian or -1
+ */
+size_t gsl_viewer_hit_workspace_bytes(void);
+int gsl_viewer_hit_test(const float *pos, const int32_t *labels, int64_t N, int stride, const double *matrix,
+                        double x, double y, double viewport_w, double viewport_h, int32_t no_selection,
+                        int32_t *label_out, int64_t *index_out, void *ws, size_t ws_bytes, void *stream);
 
 #ifdef __cplusplus
 }

@@ -47,8 +47,8 @@ assert VIEW_DTYPE.itemsize == 176
 
 def build(force: bool = False) -> str:
     """Compile the C oracle if it is missing (or `force`)."""
-    src = os.path.join(_HERE, "gsl_oracle.c")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(src) > os.path.getmtime(_LIB_PATH):
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith(".c")] + [os.path.join(_HERE, "Makefile")]
+    if force or not os.path.exists(_LIB_PATH) or max(os.path.getmtime(f) for f in srcs) > os.path.getmtime(_LIB_PATH):
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return _LIB_PATH
 
@@ -80,6 +80,14 @@ def lib() -> ctypes.CDLL:
         L.orc_kmeans_update.restype = None
         L.orc_kmeans_update_f64.argtypes = [vp, vp, i64, i32, i32, vp, vp]
         L.orc_kmeans_update_f64.restype = None
+        L.orc_viewer_depth_sort.argtypes = [vp, i64, i32, vp, vp]
+        L.orc_viewer_depth_sort.restype = None
+        L.orc_viewer_buckets.argtypes = [vp, i64, i32, vp, vp]
+        L.orc_viewer_buckets.restype = None
+        L.orc_multiply4.argtypes = [vp, vp, vp]
+        L.orc_multiply4.restype = None
+        L.orc_viewer_hit_test.argtypes = [vp, vp, i64, i32, vp, dbl, dbl, dbl, dbl, i32, vp]
+        L.orc_viewer_hit_test.restype = i32
         _lib = L
     return _lib
 
@@ -298,3 +306,136 @@ def kmeans_run(data, k, max_iter=100, tol=1e-4, init_idx=None, trace=None):
         centroids = new                                    # :88/:136
     labels = kmeans_assign(data, centroids)                # :92-96/:140-144
     return centroids, labels, it + 1
+
+
+# --------------------------------------------------------------------------------------
+# viewer-side label consumers (gaussians_selection.js, `gs`); see viewer_oracle.c
+# --------------------------------------------------------------------------------------
+NO_SELECTION = -999999          # gs:6
+
+
+def _rows(pos):
+    pos = np.ascontiguousarray(pos, np.float32)
+    assert pos.ndim == 2 and pos.shape[1] >= 3
+    return pos, pos.shape[0], pos.shape[1]
+
+
+def viewer_depth_sort(pos, view_proj) -> np.ndarray:
+    """runSort (gs:427-457).  pos f32[N][stride >= 3]; view_proj 16 doubles.  Returns depthIndex uint32[N]."""
+    pos, n, stride = _rows(pos)
+    vp_ = np.ascontiguousarray(view_proj, np.float64).reshape(16)
+    out = np.empty(n, np.uint32)
+    lib().orc_viewer_depth_sort(_ptr(pos), n, stride, _ptr(vp_), _ptr(out))
+    return out
+
+
+def viewer_buckets(pos, view_proj) -> np.ndarray:
+    pos, n, stride = _rows(pos)
+    vp_ = np.ascontiguousarray(view_proj, np.float64).reshape(16)
+    out = np.empty(n, np.int32)
+    lib().orc_viewer_buckets(_ptr(pos), n, stride, _ptr(vp_), _ptr(out))
+    return out
+
+
+def multiply4(a, b) -> np.ndarray:
+    """multiply4 (gs:110-123)."""
+    a = np.ascontiguousarray(a, np.float64).reshape(16)
+    b = np.ascontiguousarray(b, np.float64).reshape(16)
+    out = np.empty(16, np.float64)
+    lib().orc_multiply4(_ptr(a), _ptr(b), _ptr(out))
+    return out
+
+
+def viewer_hit_test(pos, labels, matrix, x, y, viewport, no_selection=NO_SELECTION):
+    """performHitTesting (gs:361-395) with the combined matrix given.  Returns (label, index)."""
+    pos, n, stride = _rows(pos)
+    labels = np.ascontiguousarray(labels, np.int32)
+    m = np.ascontiguousarray(matrix, np.float64).reshape(16)
+    idx = np.zeros(1, np.int64)
+    lab = lib().orc_viewer_hit_test(_ptr(pos), _ptr(labels), n, stride, _ptr(m), float(x), float(y),
+                                    float(viewport[0]), float(viewport[1]), int(no_selection), _ptr(idx))
+    return int(lab), int(idx[0])
+
+
+def js_to_int32_py(d: float) -> int:
+    """ECMA-262 ToInt32 on a Python float, written from the specification text."""
+    import math
+    if math.isnan(d) or math.isinf(d):
+        return 0
+    t = int(d)                      # truncation towards zero, exact
+    t %= 1 << 32
+    return t - (1 << 32) if t >= 1 << 31 else t
+
+
+def viewer_depth_sort_py(pos, view_proj):
+    """Independent pure-Python runSort (gs:427-457): Python floats are binary64 like JS numbers;
+    the typed arrays' out-of-range behaviour is written out with dictionaries."""
+    pos = np.asarray(pos, np.float32)
+    n = pos.shape[0]
+    vp_ = [float(v) for v in np.asarray(view_proj, np.float64).reshape(16)]
+    size_list = [0] * n
+    max_depth, min_depth = float("-inf"), float("inf")
+    for i in range(n):
+        x, y, z = (float(v) for v in pos[i, :3])
+        depth = js_to_int32_py((vp_[2] * x + vp_[6] * y + vp_[10] * z) * 4096)
+        size_list[i] = depth
+        max_depth = max(max_depth, depth)
+        min_depth = min(min_depth, depth)
+    with np.errstate(all="ignore"):
+        depth_inv = float(np.float64(65536.0) / np.float64(max_depth - min_depth)) if n else 0.0
+    counts0 = [0] * 65536
+    for i in range(n):
+        with np.errstate(all="ignore"):
+            size_list[i] = js_to_int32_py(float(np.float64(size_list[i] - min_depth) * np.float64(depth_inv)))
+        if 0 <= size_list[i] < 65536:
+            counts0[size_list[i]] += 1
+    starts0 = [0] * 65536
+    for i in range(1, 65536):
+        starts0[i] = starts0[i - 1] + counts0[i - 1]
+    depth_index = [0] * n
+    for i in range(n):
+        k = size_list[i]
+        if 0 <= k < 65536:          # otherwise: NaN index, nothing stored
+            depth_index[starts0[k]] = i
+            starts0[k] += 1
+    return np.array(depth_index, np.uint32)
+
+
+def viewer_hit_test_py(pos, labels, matrix, x, y, viewport, no_selection=NO_SELECTION):
+    """Independent pure-Python performHitTesting (gs:361-395)."""
+    import math
+    pos = np.asarray(pos, np.float32)
+    m = [float(v) for v in np.asarray(matrix, np.float64).reshape(16)]
+    closest_dist = closest_depth = float("inf")
+    selected, sel = no_selection, -1
+    for i in range(pos.shape[0]):
+        p = [float(pos[i, 0]), float(pos[i, 1]), float(pos[i, 2]), 1.0]
+        r = [p[0] * m[k] + p[1] * m[k + 4] + p[2] * m[k + 8] + p[3] * m[k + 12] for k in range(4)]
+        if r[3] <= 0:
+            continue
+        with np.errstate(all="ignore"):
+            w = np.float64(r[3])
+            sx = float((np.float64(r[0]) / w + 1) * 0.5 * viewport[0])
+            sy = float((np.float64(r[1]) / w + 1) * 0.5 * viewport[1])
+            depth = float(np.float64(r[2]) / w)
+        dx, dy = abs(sx - x), abs(sy - y)
+        if math.isinf(dx) or math.isinf(dy):
+            dist = float("inf")
+        elif math.isnan(dx) or math.isnan(dy):
+            dist = float("nan")
+        else:
+            mx = max(dx, dy)
+            if mx == 0:
+                dist = 0.0
+            else:                   # V8 MathHypot, Kahan loop written out
+                s = c = 0.0
+                for v in (dx, dy):
+                    q = v / mx
+                    summand = q * q - c
+                    prelim = s + summand
+                    c = (prelim - s) - summand
+                    s = prelim
+                dist = math.sqrt(s) * mx
+        if dist < 10 and (dist < closest_dist or (dist == closest_dist and depth < closest_depth)):
+            closest_dist, closest_depth, selected, sel = dist, depth, int(labels[i]), i
+    return selected, sel

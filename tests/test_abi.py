@@ -30,7 +30,7 @@ def test_library_is_built_and_exports_every_declared_symbol():
 
 def test_version_and_view_struct_size():
     native = pkg("_native")
-    assert native.lib().gsl_version() == native.ABI_VERSION == 3
+    assert native.lib().gsl_version() == native.ABI_VERSION == 4
     hdr = open(os.path.join(ROOT, "include", "gslift.h")).read()
     assert "176 bytes" in hdr and native.VIEW_DTYPE.itemsize == 176
 
@@ -113,4 +113,4 @@ int main(void)
                          "-L", lib_dir, "-lgslift", f"-Wl,-rpath,{lib_dir}"], capture_output=True, text=True)
     assert cc.returncode == 0, cc.stderr
     run = subprocess.run([str(exe)], capture_output=True, text=True)
-    assert run.returncode == 0 and "abi ok 3" in run.stdout, (run.returncode, run.stdout, run.stderr)
+    assert run.returncode == 0 and "abi ok 4" in run.stdout, (run.returncode, run.stdout, run.stderr)
