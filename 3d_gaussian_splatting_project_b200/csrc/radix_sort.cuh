@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(kThreads) histogram_kernel(const uint32_t *__r
 }
 
 // Exclusive scan of n words in place by ONE CTA of 1024 threads (n is a few hundred thousand).
-__global__ void __launch_bounds__(1024) scan_kernel(uint32_t *__restrict__ v, int64_t n)
+static __global__ void __launch_bounds__(1024) scan_kernel(uint32_t *__restrict__ v, int64_t n)
 {
     __shared__ uint32_t warp_sum[32];
     __shared__ uint32_t carry;

@@ -317,6 +317,46 @@ int gsl_viewer_hit_test(const float *pos, const int32_t *labels, int64_t N, int 
                         double x, double y, double viewport_w, double viewport_h, int32_t no_selection,
                         int32_t *label_out, int64_t *index_out, void *ws, size_t ws_bytes, void *stream);
 
+/*
+ * Normals and residuals of 3D_clustering/region_growing.py.
+ *
+ * gsl_region_knn_pca -- for every point the k nearest neighbours (itself included, as
+ * KDTree.query of a tree point returns it, rg:100), their centroid (rg:105) and, from the
+ * covariance of the centred neighbours (rg:108-111), the eigenvector of the smallest eigenvalue
+ * (rg:114-117), flipped when dot(normal, point - centroid) > 0 (rg:120-121) and normalised
+ * (rg:124); residual_i = |dot(normal_i, point_i - centroid_i)| (rg:161).
+ * The neighbour set is exact (float64 squared distances in scipy's summation order, smallest k by
+ * (distance, index); an exact distance tie at the k-th neighbour goes to the lower index where
+ * scipy's answer depends on its tree layout).  Moments are accumulated in float64 (the reference:
+ * float32 mean, float32 sgemm, LAPACK float32 eigh), so normals and residuals agree with the
+ * reference to float32 accuracy, not bit for bit.
+ *   pos         float32 [N][3], finite (scipy's KDTree rejects non-finite data as well)
+ *   k           1 <= k <= N  (rg:272-274 use 2000; rg:278 uses 10)
+ *   normals_in  optional float64 [N][3]: normals to form the residual with (compute_residuals takes
+ *               them as an argument, rg:130); NULL = the normals computed by this call
+ *   normals     optional float64 [N][3] out        residuals  optional float64 [N] out
+ *   centroids   optional float64 [N][3] out        knn        optional int32 [N][k] out, k <= 64:
+ *               neighbour indices in increasing (distance, index) order (KDTree.query order)
+ */
+size_t gsl_region_workspace_bytes(int64_t N);
+int gsl_region_knn_pca(const float *pos, int64_t N, int k, const double *normals_in, double *normals,
+                       double *residuals, double *centroids, int32_t *knn, void *ws, size_t ws_bytes,
+                       void *stream);
+
+/*
+ * segmentation_3D (rg:166-221) given the neighbour lists: HOST-side helper (no device work; the
+ * growth loop is serial by construction).  All pointers are HOST pointers.  Seeds are taken in
+ * increasing residual among the still available points (rg:193), a neighbour joins the region when
+ * |dot(n_seed, n_neighbour)| > cos(angle_threshold) (rg:205-209) and becomes a seed itself when its
+ * residual is below residual_threshold (rg:212-214).
+ *   region_of     int32 [N] out: region number of every point, in order of creation
+ *   region_sizes  optional int64 [N] out: size of every region created
+ * Returns the number of regions, or a negative GSL_E* code.
+ */
+int64_t gsl_region_grow(const int32_t *knn, int k, const double *normals, const double *residuals, int64_t N,
+                        double residual_threshold, double angle_threshold, int32_t *region_of,
+                        int64_t *region_sizes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -273,6 +273,43 @@ def make_bundled_cameras():
     print(f"[golden] bundled_cameras.json.gz: {len(bundled)} cameras")
 
 
+def region_cloud(seed, n):
+    """Three noisy planar patches and a blob: surfaces for the normals, a volume where they are ill defined."""
+    rng = np.random.default_rng(seed)
+    parts = []
+    m = n // 4
+    for axis, off in ((2, 0.0), (0, 1.5), (1, -1.0)):
+        p = rng.uniform(-1, 1, size=(m, 3))
+        p[:, axis] = off + rng.normal(0, 0.01, m)
+        parts.append(p)
+    parts.append(rng.normal(0, 0.3, size=(n - 3 * m, 3)) + [3.0, 0, 0])
+    pts = np.concatenate(parts).astype(np.float32)
+    return pts[rng.permutation(n)]
+
+
+def make_region():
+    """compute_normals / compute_residuals / segmentation_3D of region_growing.py run verbatim
+    (rg:78-221); only their progress prints are swallowed."""
+    sys.path.insert(0, os.path.join(REF, "3D_clustering"))
+    rgm = importlib.import_module("region_growing")
+    from scipy.spatial import KDTree
+    for name, seed, n, k, kseg in (("region_planes_k40", 21, 1500, 40, 10), ("region_planes_k400", 22, 1200, 400, 10),
+                                ("region_planes_k2000", 23, 2600, 2000, 10)):
+        pts = region_cloud(seed, n)
+        with contextlib.redirect_stdout(io.StringIO()):
+            normals = rgm.compute_normals(pts, k)
+            residuals = rgm.compute_residuals(pts, normals, k)
+            regions = rgm.segmentation_3D(pts, normals, residuals, residual_threshold=0.1, angle_threshold=0.05, k=kseg)
+        region_of = np.full(n, -1, np.int32)
+        for r, members in enumerate(regions):          # regions come back sorted by size, largest first (rg:219)
+            region_of[np.array(members, np.int64)] = r
+        knn_seg = KDTree(pts).query(pts, kseg)[1].astype(np.int32)      # the lists rg:203 sees
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), pos=pts, k=k, kseg=kseg, normals=normals, residuals=residuals,
+                            region_of=region_of, n_regions=len(regions), knn_seg=knn_seg,
+                            note="region_growing.py compute_normals/compute_residuals/segmentation_3D verbatim")
+        print(f"[golden] {name}: {n} points, k={k}, {len(regions)} regions")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     make_bundled_cameras()
@@ -280,6 +317,7 @@ def main():
     make_probes()
     make_lifting(dls)
     make_kmeans(km)
+    make_region()
 
 
 if __name__ == "__main__":

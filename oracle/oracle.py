@@ -88,6 +88,12 @@ def lib() -> ctypes.CDLL:
         L.orc_multiply4.restype = None
         L.orc_viewer_hit_test.argtypes = [vp, vp, i64, i32, vp, dbl, dbl, dbl, dbl, i32, vp]
         L.orc_viewer_hit_test.restype = i32
+        L.orc_region_knn_pca.argtypes = [vp, i64, i32, vp, vp, vp, vp, vp, vp]
+        L.orc_region_knn_pca.restype = None
+        L.orc_region_knn_pca_range.argtypes = [vp, i64, i32, vp, vp, vp, vp, vp, vp, i64, i64]
+        L.orc_region_knn_pca_range.restype = None
+        L.orc_region_grow.argtypes = [vp, i32, vp, vp, i64, dbl, dbl, vp]
+        L.orc_region_grow.restype = i64
         _lib = L
     return _lib
 
@@ -439,3 +445,36 @@ def viewer_hit_test_py(pos, labels, matrix, x, y, viewport, no_selection=NO_SELE
         if dist < 10 and (dist < closest_dist or (dist == closest_dist and depth < closest_depth)):
             closest_dist, closest_depth, selected, sel = dist, depth, int(labels[i]), i
     return selected, sel
+
+
+# --------------------------------------------------------------------------------------
+# region growing (3D_clustering/region_growing.py, `rg`); see region_oracle.c
+# --------------------------------------------------------------------------------------
+def region_knn_pca(pos, k, normals_in=None, want_knn=False, queries=None):
+    """compute_normals (rg:78-127) + compute_residuals (rg:130-163) for one k; `queries` = (q0, q1)
+    restricts the work to those points (the other rows of the outputs are left uninitialised).
+    Returns dict(normals f64[N,3], residuals f64[N], centroids f32[N,3], gap f64[N], knn int32[N,k] or None)."""
+    pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 3)
+    n = pos.shape[0]
+    normals = np.empty((n, 3), np.float64)
+    residuals = np.empty(n, np.float64)
+    centroids = np.empty((n, 3), np.float32)
+    gap = np.empty(n, np.float64)
+    knn = np.empty((n, k), np.int32) if want_knn else None
+    nin = None if normals_in is None else np.ascontiguousarray(normals_in, np.float64)
+    q0, q1 = (0, n) if queries is None else (int(queries[0]), int(queries[1]))
+    lib().orc_region_knn_pca_range(_ptr(pos), n, int(k), _ptr(nin) if nin is not None else None, _ptr(normals), _ptr(residuals),
+                                   _ptr(centroids), _ptr(knn) if want_knn else None, _ptr(gap), q0, q1)
+    return dict(normals=normals, residuals=residuals, centroids=centroids, gap=gap, knn=knn)
+
+
+def region_grow(knn, normals, residuals, residual_threshold, angle_threshold):
+    """segmentation_3D (rg:166-221) given neighbour lists.  Returns region_of int32[N] (creation order)."""
+    knn = np.ascontiguousarray(knn, np.int32)
+    normals = np.ascontiguousarray(normals, np.float64)
+    residuals = np.ascontiguousarray(residuals, np.float64)
+    n, k = knn.shape
+    region_of = np.empty(n, np.int32)
+    r = lib().orc_region_grow(_ptr(knn), k, _ptr(normals), _ptr(residuals), n, float(residual_threshold),
+                              float(angle_threshold), _ptr(region_of))
+    return region_of, int(r)
