@@ -88,7 +88,9 @@ def test_random_clouds_equal_oracle(oracle, n, k):
     got = rg.knn_pca(pos, k, want_centroids=True, want_knn=k <= 64)
     if k <= 64:
         assert np.array_equal(got["knn"].cpu().numpy(), ref["knn"])
-    assert np.abs(got["centroids"].cpu().numpy() - ref["centroids"]).max() < 2e-6
+    # the reference's centroid is a float32 SEQUENTIAL mean (rg:105): its own rounding grows with k
+    # (~ sqrt(k) ulps of the running sum), the GPU's float64 sum does not drift
+    assert np.abs(got["centroids"].cpu().numpy() - ref["centroids"]).max() < (2e-6 if k <= 64 else 2e-5)
     if k >= 7:
         check_against(oracle, pos, k, got["normals"].cpu().numpy(), got["residuals"].cpu().numpy(), ref)
 
@@ -105,7 +107,7 @@ def test_outliers_duplicates_and_degenerate_sets(oracle):
         if k <= 64:
             assert np.array_equal(got["knn"].cpu().numpy(), ref["knn"])
         scale = np.abs(ref["centroids"]).max(1) + 1
-        assert (np.abs(got["centroids"].cpu().numpy() - ref["centroids"]).max(1) / scale).max() < 1e-6
+        assert (np.abs(got["centroids"].cpu().numpy() - ref["centroids"]).max(1) / scale).max() < 1e-5
     # duplicated points: exact distance ties at the k-th neighbour go to the lower index on both sides
     base = _blobs(rng, 500)
     dup = np.concatenate((base, base, base[:100]))[rng.permutation(1100)]
