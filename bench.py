@@ -67,6 +67,7 @@ def parse_args():
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true", help="no CPU oracle legs (parity and cpu_baseline become null)")
     ap.add_argument("--skip-kmeans", action="store_true")
+    ap.add_argument("--skip-next", action="store_true", help="no section-8f rows (viewer depth sort / hit test, region-growing normals)")
     return ap.parse_args()
 
 
@@ -188,6 +189,74 @@ def cpu_kmeans_sample(a, orc, data, cen):
     orc.kmeans_update(data, lab, cen)
     dt = time.perf_counter() - t0
     return 1.0 / (dt * a.kmeans_rows / len(data)), dt, lab
+
+
+def next_rows(a, gs, orc, pos, labels_host, dev):
+    """SURVEY section 8f rows N3 / N4 on one GPU: the viewer worker's depth sort and click hit test over the
+    bench cloud, and region_growing.py's normals (k = 2000) over its first 200 000 points; each checked
+    against the oracle (when available) and timed with CUDA events, the oracle timed beside it."""
+    import torch
+    viewer, rgrow = gs.viewer, importlib.import_module(gs.__name__ + ".region_growing")
+    out = {}
+    dpos = torch.from_numpy(pos).to(dev)
+    dlab = torch.from_numpy(np.ascontiguousarray(labels_host, np.int32)).to(dev)
+    n = int(dpos.shape[0])
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            r = fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return r, e0.elapsed_time(e1) / reps
+
+    view = [1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 6.0, 1.0]              # cloud pushed to z = 6 (column-major)
+    proj = [1.2, 0, 0, 0, 0, 1.2 * 16 / 9, 0, 0, 0, 0, 1.01, 1.0, 0, 0, -0.2, 0]
+    vp = viewer.multiply4(proj, view)
+    order, ms = timed(lambda: viewer.run_sort(dpos, vp), 10)
+    row = {"gaussians": n, "ms": ms, "gaussians_per_s": n / (ms * 1e-3), "kernels": "depth + bucket + 2 x (histogram, scan, scatter)"}
+    if orc is not None:
+        t0 = time.perf_counter()
+        want = orc.viewer_depth_sort(pos, vp)
+        row["cpu_ms"] = (time.perf_counter() - t0) * 1e3
+        row["equals_oracle"] = bool(np.array_equal(order.cpu().numpy(), want))
+    out["viewer_depth_sort (gaussians_selection.js:417-462)"] = row
+
+    clicks = [(960.0, 540.0), (700.5, 400.25), (1200.0, 650.0), (10.0, 10.0)]
+    def hits():
+        return [viewer.perform_hit_testing(x, y, view, proj, (1920, 1080), dpos, dlab, return_index=True) for x, y in clicks]
+    got, ms = timed(hits, 3)
+    row = {"gaussians": n, "clicks": len(clicks), "ms_per_click": ms / len(clicks), "selected": [g[1] for g in got],
+           "note": "per click: project all Gaussians, reduce, read the label back (one host sync)"}
+    if orc is not None:
+        t0 = time.perf_counter()
+        want = [orc.viewer_hit_test(pos, labels_host, vp, x, y, (1920, 1080)) for x, y in clicks]
+        row["cpu_ms_per_click"] = (time.perf_counter() - t0) * 1e3 / len(clicks)
+        row["equals_oracle"] = bool(got == want)
+    out["viewer_hit_test (gaussians_selection.js:361-395)"] = row
+
+    m, k = min(200_000, n), 2000
+    if m >= k:
+        sub = dpos[:m].contiguous()
+        res, ms = timed(lambda: rgrow.knn_pca(sub, k), 2)
+        row = {"points": m, "k": k, "ms": ms, "points_per_s": m / (ms * 1e-3),
+               "note": "normals + residuals of region_growing.py compute_normals / compute_residuals (k = 2000 as in its __main__)"}
+        if orc is not None:
+            q0, q1 = m // 2, m // 2 + 200
+            t0 = time.perf_counter()
+            ref = orc.region_knn_pca(pos[:m], k, queries=(q0, q1))
+            cpu_s = time.perf_counter() - t0
+            ok = ref["gap"][q0:q1] > 1e-2
+            dots = (res["normals"][q0:q1].cpu().numpy() * ref["normals"][q0:q1]).sum(1)
+            row["cpu_ms_scaled_to_all_points"] = cpu_s * 1e3 * m / (q1 - q0)
+            row["cpu_sample"] = f"{q1 - q0} queries, brute-force C/OpenMP oracle on {orc.max_threads()} threads"
+            row["max_1_minus_abs_cos_vs_oracle"] = float((1 - np.abs(dots[ok])).max()) if ok.any() else None
+            row["max_abs_residual_diff_vs_oracle"] = float(np.abs(res["residuals"][q0:q1].cpu().numpy() - ref["residuals"][q0:q1])[ok].max()) if ok.any() else None
+        out["region_knn_pca (region_growing.py:78-163)"] = row
+    return out
 
 
 def run_reference(a):
@@ -490,6 +559,10 @@ def run_native(a):
                "labels_equal_resident_run": same, "staging": staging,
                "call": "deep_learning_segmentation.lift_labels(positions, cameras, seg_maps) with pinned host int32 maps"}
 
+    nxt = None
+    if world == 1 and not a.skip_next:
+        nxt = next_rows(a, gs, orc, pos, labels.cpu().numpy(), dev)
+
     if rank == 0:
         peak, peak_src = peak_hbm()
         alg_bytes = 16 * n_r + V * H * W
@@ -512,7 +585,7 @@ def run_native(a):
             "roofline_step": {"bound": "hbm", "achieved": ach_step, "peak": peak, "unit": "GB/s", "frac": ach_step / peak,
                               "note": "same algorithmic bytes over the whole step (prepare + gather + majority)"},
             "parity": parity,
-            "cpu_baseline": cpu, "e2e": e2e, "kmeans": kres,
+            "cpu_baseline": cpu, "e2e": e2e, "kmeans": kres, "next_rows": nxt,
             "gpu_launches": int(n_lift_launches),
             "gpu_launches_note": "counted by the library (gsl_launch_count) around the timed lifting region; the radix sort's CUB kernels (5 per step) are not in the count",
             "clocks": clocks, "clocks_window": "lifting + k-means timed regions, nvidia-smi -lms 20", "label_histogram_head": label_hist,
