@@ -67,7 +67,7 @@ SIGNATURES = {
     "gsl_viewer_sort_workspace_bytes": (_sz, [_i64]),
     "gsl_viewer_depth_sort": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
     "gsl_region_workspace_bytes": (_sz, [_i64]),
-    "gsl_region_knn_pca": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "gsl_region_knn_pca": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gsl_region_grow": (_i64, [_vp, _i32, _vp, _vp, _i64, _dbl, _dbl, _vp, _vp]),
     "gsl_viewer_hit_workspace_bytes": (_sz, []),
     "gsl_viewer_hit_test": (_i32, [_vp, _vp, _i64, _i32, _vp, _dbl, _dbl, _dbl, _dbl, _i32, _vp, _vp, _vp, _sz, _vp]),

@@ -1,5 +1,5 @@
 // Stable least-significant-digit radix sort of (uint32 key, uint32 payload) pairs, hand written
-// for sm_100a (no library).  One pass = histogram kernel + scan kernel + scatter kernel:
+// for sm_100a (no library).  One pass = histogram kernel + row-scan kernel + scatter kernel:
 //
 //   tile     = THREADS x ITEMS consecutive pairs; warp w of the tile owns a contiguous run of
 //              32 x ITEMS pairs and walks it in rounds of 32 consecutive pairs (lane = pair), so
@@ -7,7 +7,8 @@
 //   ranking  = in a round, __match_any_sync groups the lanes holding the same digit; a lane's
 //              rank is the per-warp running count of its digit plus the number of lower lanes
 //              of its group -- no atomics, and the rank order is the input order (stability).
-//   bases    = hist[digit][tile] scanned in that (digit-major) order by one CTA.
+//   bases    = hist[digit][tile]: one CTA per digit scans its row and adds the number of pairs with
+//              a smaller digit (digit totals are accumulated by the histogram kernel).
 //
 // Used by the viewer-side depth sort (viewer.cu: 17-bit bucket keys, two 9-bit passes) and by
 // the k-nearest-neighbour grid of region_growing.cu.
@@ -27,7 +28,7 @@ constexpr int kWarps = kThreads / 32;
 
 inline int n_tiles(int64_t N) { return (int)((N + kTile - 1) / kTile); }
 // uint32 words of histogram scratch one pass of `bits` bits needs.
-inline size_t hist_words(int64_t N, int bits) { return ((size_t)n_tiles(N) << bits) + 1; }
+inline size_t hist_words(int64_t N, int bits) { return ((size_t)n_tiles(N) << bits) + ((size_t)1 << bits); }
 
 __device__ __forceinline__ unsigned lanemask_lt()
 {
@@ -67,76 +68,69 @@ __device__ __forceinline__ void rank_warp_run(const uint32_t *__restrict__ keys,
 
 template <int BITS>
 __global__ void __launch_bounds__(kThreads) histogram_kernel(const uint32_t *__restrict__ keys, int64_t N, int shift,
-                                                             uint32_t *__restrict__ hist, int tiles)
+                                                             uint32_t *__restrict__ hist, uint32_t *__restrict__ total, int tiles)
 {
     constexpr int DIG = 1 << BITS;
-    __shared__ uint32_t cnt[DIG];
-    for (int d = threadIdx.x; d < DIG; d += kThreads) cnt[d] = 0;
+    // two private copies (even / odd warps) halve the collisions of the shared-memory atomics
+    __shared__ uint32_t cnt[2][DIG];
+    for (int d = threadIdx.x; d < 2 * DIG; d += kThreads) (&cnt[0][0])[d] = 0;
     __syncthreads();
     const int tile = blockIdx.x;
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, lt = lanemask_lt();
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const int64_t warp_begin = (int64_t)tile * kTile + (int64_t)warp * 32 * kItems;
-#pragma unroll 4
+    uint32_t *mine = cnt[warp & 1];
+#pragma unroll
     for (int r = 0; r < kItems; ++r) {
         const int64_t i = warp_begin + r * 32 + lane;
-        const bool valid = i < N;
-        const unsigned act = __ballot_sync(0xffffffffu, valid);
-        if (valid) {
-            const uint32_t d = (keys[i] >> shift) & (uint32_t)(DIG - 1);
-            const unsigned peers = __match_any_sync(act, d);
-            if ((peers & lt) == 0) atomicAdd(&cnt[d], (uint32_t)__popc(peers));
-        }
+        if (i < N) atomicAdd(&mine[(keys[i] >> shift) & (uint32_t)(DIG - 1)], 1u);
     }
     __syncthreads();
-    for (int d = threadIdx.x; d < DIG; d += kThreads) hist[(size_t)d * tiles + tile] = cnt[d];
+    for (int d = threadIdx.x; d < DIG; d += kThreads) {
+        const uint32_t c = cnt[0][d] + cnt[1][d];
+        hist[(size_t)d * tiles + tile] = c;
+        if (c) atomicAdd(&total[d], c);
+    }
 }
 
-// Exclusive scan of n words in place by ONE CTA of 1024 threads (n is a few hundred thousand).
-static __global__ void __launch_bounds__(1024) scan_kernel(uint32_t *__restrict__ v, int64_t n)
+// hist[d][0..tiles) <- exclusive scan of the row, offset by the number of pairs with a smaller digit.
+// One CTA per digit.
+template <int BITS>
+__global__ void __launch_bounds__(256) scan_rows_kernel(uint32_t *__restrict__ hist, const uint32_t *__restrict__ total, int tiles)
 {
-    __shared__ uint32_t warp_sum[32];
+    __shared__ uint32_t warp_sum[8];
     __shared__ uint32_t carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
+    const int d = blockIdx.x;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    // chunks of 1024 x 4 words, lane-contiguous 16-byte pieces would need alignment of n; plain
-    // coalesced words are enough for a table this small
-    for (int64_t base = 0; base < n; base += 1024 * 4) {
-        uint32_t x[4], s = 0;
+    uint32_t below = 0;
+    for (int j = threadIdx.x; j < d; j += 256) below += total[j];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int64_t i = base + (int64_t)threadIdx.x * 4 + j;
-            x[j] = i < n ? v[i] : 0u;
-            s += x[j];
-        }
-        uint32_t inc = s;
+    for (int o = 16; o; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
+    if (lane == 0) warp_sum[warp] = below;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t b = 0;
+        for (int w = 0; w < 8; ++w) b += warp_sum[w];
+        carry = b;
+    }
+    __syncthreads();
+    uint32_t *row = hist + (size_t)d * tiles;
+    for (int base = 0; base < tiles; base += 256) {
+        const int i = base + (int)threadIdx.x;
+        const uint32_t x = i < tiles ? row[i] : 0u;
+        uint32_t inc = x;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
             if (lane >= (unsigned)o) inc += t;
         }
+        __syncthreads();                      // previous round's warp_sum / carry reads are done
         if (lane == 31) warp_sum[warp] = inc;
         __syncthreads();
-        if (warp == 0) {
-            uint32_t w = warp_sum[lane], wi = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
-                if (lane >= (unsigned)o) wi += t;
-            }
-            warp_sum[lane] = wi - w;      // exclusive over warps
-        }
+        uint32_t before = carry;
+        for (unsigned w = 0; w < warp; ++w) before += warp_sum[w];
+        if (i < tiles) row[i] = before + inc - x;
         __syncthreads();
-        uint32_t run = carry + warp_sum[warp] + (inc - s);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int64_t i = base + (int64_t)threadIdx.x * 4 + j;
-            if (i < n) v[i] = run;
-            run += x[j];
-        }
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = run;
-        __syncthreads();
+        if (threadIdx.x == 255) carry = before + inc;
     }
 }
 
@@ -193,10 +187,12 @@ inline int pass(const uint32_t *keys, const uint32_t *pay_in, uint32_t *keys_out
 {
     if (N <= 0) return GSL_OK;
     const int tiles = n_tiles(N);
-    histogram_kernel<BITS><<<tiles, kThreads, 0, st>>>(keys, N, shift, hist, tiles);
+    uint32_t *total = hist + ((size_t)tiles << BITS);
+    GSL_CUDA_TRY(cudaMemsetAsync(total, 0, sizeof(uint32_t) << BITS, st));
+    histogram_kernel<BITS><<<tiles, kThreads, 0, st>>>(keys, N, shift, hist, total, tiles);
     GSL_LAUNCH_CHECK("radix::histogram_kernel");
-    scan_kernel<<<1, 1024, 0, st>>>(hist, (int64_t)tiles << BITS);
-    GSL_LAUNCH_CHECK("radix::scan_kernel");
+    scan_rows_kernel<BITS><<<1 << BITS, 256, 0, st>>>(hist, total, tiles);
+    GSL_LAUNCH_CHECK("radix::scan_rows_kernel");
     scatter_kernel<BITS><<<tiles, kThreads, 0, st>>>(keys, pay_in, keys_out, pay_out, N, shift, hist, tiles, drop_key,
                                                      drop_payload);
     GSL_LAUNCH_CHECK("radix::scatter_kernel");

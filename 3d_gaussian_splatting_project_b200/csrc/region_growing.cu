@@ -22,9 +22,10 @@
 // grids of 2^L cells per axis, L = 1..7, each with a dense cell-start table.  A warp owns a query:
 // it looks for the finest (level, ring) whose cube of (2*ring+1)^3 cells provably contains the k
 // nearest neighbours (at least k points within ring * cell_size of the query), then selects the
-// k-th smallest squared distance by an 11-bit-per-pass radix select over the float64 bit
-// patterns (per-warp histogram in shared memory), and accumulates the moments of the selected
-// points.  Each step is a walk over the cube's non-empty cell ranges, kept in shared memory.
+// k-th smallest squared distance by a 10-bit-per-walk radix select over the float64 bit
+// patterns, rebased so that the leading digit resolves [R^2 / 1024, R^2] (per-warp histogram in
+// shared memory; the first digit is counted by the walk that validates the cube), and accumulates
+// the moments of the selected points.  Each step is a walk over the cube's non-empty cell ranges, kept in shared memory.
 #include <float.h>
 #include <math.h>
 #include <math_constants.h>
@@ -42,7 +43,7 @@ namespace rg {
 
 constexpr int kLevels = 7;                 // finest grid: 128 cells per axis
 constexpr int kFinest = 1 << kLevels;
-constexpr int kDigitBits = 11;
+constexpr int kDigitBits = 10;
 constexpr int kDigits = 1 << kDigitBits;
 constexpr int kWarps = 8;
 constexpr int kMaxRanges = 343;            // (2 * 3 + 1)^3 cells
@@ -110,15 +111,35 @@ __global__ void __launch_bounds__(256) bbox_kernel(const float *__restrict__ pos
     }
 }
 
-__global__ void bbox_final_kernel(const float *__restrict__ part, int n, GridInfo *__restrict__ g)
+__global__ void __launch_bounds__(256) bbox_final_kernel(const float *__restrict__ part, int n, GridInfo *__restrict__ g)
 {
-    if (threadIdx.x != 0) return;
-    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-    for (int b = 0; b < n; ++b)
-        for (int a = 0; a < 3; ++a) {
-            lo[a] = fminf(lo[a], part[b * 6 + a]);
-            hi[a] = fmaxf(hi[a], part[b * 6 + 3 + a]);
+    __shared__ float s[8][6];
+    float v[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) v[a] = a < 3 ? FLT_MAX : -FLT_MAX;
+    for (int b = threadIdx.x; b < n; b += 256)
+#pragma unroll
+        for (int a = 0; a < 6; ++a) v[a] = a < 3 ? fminf(v[a], part[b * 6 + a]) : fmaxf(v[a], part[b * 6 + a]);
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const float t = __shfl_xor_sync(0xffffffffu, v[a], o);
+            v[a] = a < 3 ? fminf(v[a], t) : fmaxf(v[a], t);
         }
+        if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5][a] = v[a];
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    float lo[3], hi[3];
+    for (int a = 0; a < 3; ++a) {
+        lo[a] = s[0][a];
+        hi[a] = s[0][3 + a];
+        for (int w = 1; w < 8; ++w) {
+            lo[a] = fminf(lo[a], s[w][a]);
+            hi[a] = fmaxf(hi[a], s[w][3 + a]);
+        }
+    }
     double side = 0;
     for (int a = 0; a < 3; ++a) side = fmax(side, (double)hi[a] - (double)lo[a]);
     if (!(side > 0)) side = 1.0;                       // all points coincide
@@ -176,7 +197,8 @@ struct QueryOut {
 
 struct WarpScratch {
     uint32_t hist[kDigits];
-    uint2 ranges[kMaxRanges + 1];
+    uint32_t end[kMaxRanges + 1];      // end[r] = points in ranges 0..r (inclusive prefix of the range lengths)
+    uint32_t off[kMaxRanges + 1];      // off[r] = start of range r in the sorted array - points before range r
     double list_d[kMaxList];
     uint32_t list_i[kMaxList];
 };
@@ -187,13 +209,17 @@ __device__ __forceinline__ double sqdist(const float4 p, double qx, double qy, d
     return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
 }
 
-// Non-empty cell ranges of the cube of `ring` cells around (cx, cy, cz) at level L into sc.ranges.
-// Returns their number; *total = points in the cube.  L == 0: the whole array.
+// Non-empty cell ranges of the cube of `ring` cells around (cx, cy, cz) at level L, as a flat index
+// space: candidate v (0 <= v < total) is sorted[off[r] + v] for the r with end[r - 1] <= v < end[r].
+// Returns the number of ranges; *total = points in the cube.  L == 0: the whole array.
 __device__ int build_ranges(const Tables &T, int64_t N, int L, int ring, int cx, int cy, int cz, WarpScratch &sc,
                             unsigned lane, int64_t *total)
 {
     if (L == 0) {
-        if (lane == 0) sc.ranges[0] = make_uint2(0u, (uint32_t)N);
+        if (lane == 0) {
+            sc.end[0] = (uint32_t)N;
+            sc.off[0] = 0u;
+        }
         __syncwarp();
         *total = N;
         return 1;
@@ -204,7 +230,7 @@ __device__ int build_ranges(const Tables &T, int64_t N, int L, int ring, int cx,
     const int nx = x1 - x0 + 1, ny = y1 - y0 + 1, ncell = nx * ny * (z1 - z0 + 1);
     const uint32_t *start = T.start[L];
     int cnt = 0;
-    int64_t tot = 0;
+    uint32_t tot = 0;
     for (int base = 0; base < ncell; base += 32) {
         const int id = base + (int)lane;
         uint32_t s = 0, e = 0;
@@ -214,30 +240,54 @@ __device__ int build_ranges(const Tables &T, int64_t N, int L, int ring, int cx,
             s = start[c];
             e = start[c + 1];
         }
-        const unsigned full = __ballot_sync(0xffffffffu, e > s);
-        if (e > s) sc.ranges[cnt + __popc(full & radix::lanemask_lt())] = make_uint2(s, e);
-        cnt += __popc(full);
-        tot += e - s;
-    }
+        const uint32_t len = e - s;
+        uint32_t inc = len;                       // inclusive prefix of the lengths over the lanes
 #pragma unroll
-    for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (unsigned)o) inc += t;
+        }
+        const unsigned full = __ballot_sync(0xffffffffu, len != 0);
+        if (len != 0) {
+            const int at = cnt + __popc(full & radix::lanemask_lt());
+            sc.end[at] = tot + inc;
+            sc.off[at] = s - (tot + inc - len);
+        }
+        cnt += __popc(full);
+        tot += __shfl_sync(0xffffffffu, inc, 31);
+    }
     __syncwarp();
     *total = tot;
     return cnt;
 }
 
-// Calls f(valid, point) for every point of the ranges, all 32 lanes in lockstep.
+// Calls f(valid, point) for every point of the ranges, all 32 lanes in lockstep and all lanes busy: lane l
+// takes candidates l, l + 32, ... of the flat index space and advances its own range cursor.
 template <class F>
-__device__ __forceinline__ void walk(const float4 *__restrict__ sorted, const WarpScratch &sc, int n_ranges, unsigned lane, F f)
+__device__ __forceinline__ void walk(const float4 *__restrict__ sorted, const WarpScratch &sc, uint32_t total, unsigned lane, F f)
 {
-    for (int r = 0; r < n_ranges; ++r) {
-        const uint2 se = sc.ranges[r];
-        for (uint32_t base = se.x; base < se.y; base += 32) {
-            const uint32_t j = base + lane;
-            const bool valid = j < se.y;
-            const float4 p = valid ? sorted[j] : make_float4(0.f, 0.f, 0.f, 0.f);
-            f(valid, p);
+    if (total == 0) return;
+    constexpr int U = 4;                    // independent loads in flight per lane
+    int r = 0;
+    uint32_t r_end = sc.end[0], off = sc.off[0];
+    for (uint32_t v0 = 0; v0 < total; v0 += 32 * U) {
+        float4 p[U];
+        bool valid[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t v = v0 + 32 * u + lane;
+            valid[u] = v < total;
+            const uint32_t vv = valid[u] ? v : total - 1;
+            while (vv >= r_end) {
+                ++r;
+                r_end = sc.end[r];
+                off = sc.off[r];
+            }
+            p[u] = __ldg(sorted + (off + vv));
         }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (v0 + 32 * u < total) f(valid[u], p[u]);      // warp-uniform condition
     }
 }
 
@@ -293,7 +343,7 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
-__global__ void __launch_bounds__(kWarps * 32) knn_pca_kernel(const float4 *__restrict__ sorted, int64_t N, int k,
+__global__ void __launch_bounds__(kWarps * 32, 2) knn_pca_kernel(const float4 *__restrict__ sorted, int64_t N, int k,
                                                               const GridInfo *__restrict__ ginfo, Tables T, QueryOut out,
                                                               unsigned long long *__restrict__ stats)
 {
@@ -309,31 +359,61 @@ __global__ void __launch_bounds__(kWarps * 32) knn_pca_kernel(const float4 *__re
         const int c7x = cell_coord(qx, G.lo[0], G.inv_h7), c7y = cell_coord(qy, G.lo[1], G.inv_h7),
                   c7z = cell_coord(qz, G.lo[2], G.inv_h7);
 
-        // 1. the finest cube that provably holds the k nearest neighbours
+        // Key of a squared distance: its float64 bit pattern (monotone for d2 >= 0), clamped from below at
+        // `floor_bits` and rebased there.  With floor = R2 / 1024 the leading 10-bit digit resolves the range
+        // [R2 / 1024, R2], where the k-th distance almost always lies, into ~640 bins (64 per binade) instead of
+        // spending a walk on the exponent field; the histogram's atomics then rarely collide.
+        unsigned long long floor_bits = 0;
+        int top_shift = 54;                 // raw keys (floor_bits == 0) are below 2^63: leading digit = bits 63..54
+        auto key_of = [&](double d2) -> unsigned long long {
+            const unsigned long long b = (unsigned long long)__double_as_longlong(d2);
+            return (b > floor_bits ? b : floor_bits) - floor_bits;
+        };
+        unsigned long long n_walks = 0, n_walked = 0;
+
+        // 1. the finest cube that provably holds the k nearest neighbours; the counting walk also fills the
+        //    histogram of the leading digit
         int n_ranges = 0;
+        int64_t in_cube = 0;
         double R2 = CUDART_INF;
+        bool have_hist = false;
         for (int L = kLevels; L >= 0; --L) {
             bool found = false;
             for (int ring = (L == kLevels ? 1 : 2); ring <= 3; ++ring) {
-                int64_t total = 0;
                 n_ranges = build_ranges(T, N, L, ring, c7x >> (kLevels - L), c7y >> (kLevels - L), c7z >> (kLevels - L), sc, lane,
-                                        &total);
+                                        &in_cube);
                 if (L == 0) {
                     R2 = CUDART_INF;
+                    floor_bits = 0;
+                    top_shift = 54;
                     found = true;
                     break;
                 }
-                if (total < k) continue;
+                if (in_cube < k) continue;
                 // every point outside the cube is farther than ring cells of this level
                 const double rad = (double)ring * G.h7 * (double)(1 << (kLevels - L)) * (1.0 - 1e-9);
                 R2 = rad * rad;
+                const unsigned long long r2_bits = (unsigned long long)__double_as_longlong(R2);
+                const bool clamp = r2_bits > (11ull << 52);
+                floor_bits = clamp ? r2_bits - (10ull << 52) : 0ull;          // bits of R2 / 1024
+                top_shift = clamp ? 46 : 54;                                   // clamped keys are <= 10 * 2^52 < 2^56
+                for (int d = lane; d < kDigits; d += 32) sc.hist[d] = 0;
+                __syncwarp();
                 int inside = 0;
-                walk(sorted, sc, n_ranges, lane, [&](bool valid, const float4 p) {
-                    inside += (valid && sqdist(p, qx, qy, qz) <= R2) ? 1 : 0;
+                walk(sorted, sc, (uint32_t)in_cube, lane, [&](bool valid, const float4 p) {
+                    const double d2 = sqdist(p, qx, qy, qz);
+                    if (valid && d2 <= R2) {
+                        ++inside;
+                        atomicAdd(&sc.hist[(unsigned)(key_of(d2) >> top_shift)], 1u);
+                    }
                 });
+                ++n_walks;
+                n_walked += (unsigned long long)in_cube;
 #pragma unroll
                 for (int o = 16; o; o >>= 1) inside += __shfl_xor_sync(0xffffffffu, inside, o);
+                __syncwarp();
                 if (inside >= k) {
+                    have_hist = true;
                     found = true;
                     break;
                 }
@@ -341,26 +421,31 @@ __global__ void __launch_bounds__(kWarps * 32) knn_pca_kernel(const float4 *__re
             if (found) break;
         }
 
-        // 2. radix select of the k-th smallest squared distance among the points within R2
+        // 2. radix select of the k-th smallest key among the points within R2, 10 bits per walk
         unsigned long long prefix = 0;      // the digits chosen so far = key >> shift
-        int shift = 64, need = k;
+        int shift = top_shift + kDigitBits, need = k;
         bool exact = false;                 // every key with (key >> shift) <= prefix is selected
+        bool first = true;
         while (shift > 0 && !exact) {
             const int bits = shift >= kDigitBits ? kDigitBits : shift;
             const int new_shift = shift - bits;
-            for (int d = lane; d < kDigits; d += 32) sc.hist[d] = 0;
-            __syncwarp();
-            const bool first = shift == 64;
-            walk(sorted, sc, n_ranges, lane, [&](bool valid, const float4 p) {
-                const double d2 = sqdist(p, qx, qy, qz);
-                const unsigned long long key = (unsigned long long)__double_as_longlong(d2);
-                if (valid && d2 <= R2 && (first || (key >> shift) == prefix))
-                    atomicAdd(&sc.hist[(unsigned)(key >> new_shift) & ((1u << bits) - 1u)], 1u);
-            });
-            __syncwarp();
-            // locate the digit holding the need-th smallest: lane l owns bins [64 l, 64 l + 64)
+            if (!(first && have_hist)) {
+                for (int d = lane; d < kDigits; d += 32) sc.hist[d] = 0;
+                __syncwarp();
+                walk(sorted, sc, (uint32_t)in_cube, lane, [&](bool valid, const float4 p) {
+                    const double d2 = sqdist(p, qx, qy, qz);
+                    const unsigned long long key = key_of(d2);
+                    if (valid && d2 <= R2 && (first || (key >> shift) == prefix))
+                        atomicAdd(&sc.hist[(unsigned)(key >> new_shift) & ((1u << bits) - 1u)], 1u);
+                });
+                ++n_walks;
+                n_walked += (unsigned long long)in_cube;
+                __syncwarp();
+            }
+            // locate the digit holding the need-th smallest: lane l owns bins [32 l, 32 l + 32)
+            constexpr int kPerLane = kDigits / 32;
             uint32_t mine = 0;
-            for (int d = 0; d < kDigits / 32; ++d) mine += sc.hist[lane * (kDigits / 32) + d];
+            for (int d = 0; d < kPerLane; ++d) mine += sc.hist[lane * kPerLane + d];
             uint32_t inc = mine;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -372,10 +457,10 @@ __global__ void __launch_bounds__(kWarps * 32) knn_pca_kernel(const float4 *__re
             int digit = 0, below = 0, bucket = 0;
             if ((int)lane == owner) {
                 uint32_t run = inc - mine;
-                for (int d = 0; d < kDigits / 32; ++d) {
-                    const uint32_t h = sc.hist[lane * (kDigits / 32) + d];
+                for (int d = 0; d < kPerLane; ++d) {
+                    const uint32_t h = sc.hist[lane * kPerLane + d];
                     if (run + h >= (uint32_t)need) {
-                        digit = lane * (kDigits / 32) + d;
+                        digit = lane * kPerLane + d;
                         below = run;
                         bucket = h;
                         break;
@@ -386,11 +471,20 @@ __global__ void __launch_bounds__(kWarps * 32) knn_pca_kernel(const float4 *__re
             digit = __shfl_sync(0xffffffffu, digit, owner);
             below = __shfl_sync(0xffffffffu, below, owner);
             bucket = __shfl_sync(0xffffffffu, bucket, owner);
+            __syncwarp();
+            if (first && floor_bits != 0 && digit == 0) {
+                // the k-th distance is below the clamp (tiny k): select again on the raw bit patterns
+                floor_bits = 0;
+                top_shift = 54;
+                shift = top_shift + kDigitBits;
+                have_hist = false;
+                continue;
+            }
             need -= below;
             prefix = (prefix << bits) | (unsigned long long)digit;
             shift = new_shift;
             exact = need == bucket;
-            __syncwarp();
+            first = false;
         }
         // here: keys with (key >> shift) < prefix are all selected; of those equal to prefix, `need` are
         // (all of them when `exact`; otherwise shift == 0 and they are exact ties: lowest indices win)
@@ -418,23 +512,25 @@ __global__ void __launch_bounds__(kWarps * 32) knn_pca_kernel(const float4 *__re
                 n_list += __popc(m);
             }
         };
-        walk(sorted, sc, n_ranges, lane, [&](bool valid, const float4 p) {
+        walk(sorted, sc, (uint32_t)in_cube, lane, [&](bool valid, const float4 p) {
             const double d2 = sqdist(p, qx, qy, qz);
-            const unsigned long long key = (unsigned long long)__double_as_longlong(d2) >> shift;
+            const unsigned long long key = key_of(d2) >> shift;
             const bool sel = valid && d2 <= R2 && (exact ? key <= prefix : key < prefix);
             take(sel, p, d2);
         });
+        ++n_walks;
+        n_walked += (unsigned long long)in_cube;
         if (!exact) {
             // exact ties at the k-th distance: take the `need` lowest original indices among them
             long long last = -1;
             for (int t = 0; t < need; ++t) {
                 unsigned long long best = ~0ull;      // (index << 32) | sorted position is not needed: index is unique
                 float4 bp = make_float4(0.f, 0.f, 0.f, 0.f);
-                walk(sorted, sc, n_ranges, lane, [&](bool valid, const float4 p) {
+                walk(sorted, sc, (uint32_t)in_cube, lane, [&](bool valid, const float4 p) {
                     const double d2 = sqdist(p, qx, qy, qz);
-                    const unsigned long long key = (unsigned long long)__double_as_longlong(d2);
+                    const unsigned long long key = key_of(d2);
                     const long long idx = (long long)__float_as_uint(p.w);
-                    if (valid && key == prefix && idx > last && (unsigned long long)idx < best) {
+                    if (valid && d2 <= R2 && key == prefix && idx > last && (unsigned long long)idx < best) {
                         best = (unsigned long long)idx;
                         bp = p;
                     }
@@ -442,7 +538,9 @@ __global__ void __launch_bounds__(kWarps * 32) knn_pca_kernel(const float4 *__re
                 unsigned long long wbest = best;
 #pragma unroll
                 for (int o = 16; o; o >>= 1) wbest = min(wbest, __shfl_xor_sync(0xffffffffu, wbest, o));
-                take(best == wbest && best != ~0ull, bp, __longlong_as_double((long long)prefix));
+                take(best == wbest && best != ~0ull, bp, __longlong_as_double((long long)(prefix + floor_bits)));
+                ++n_walks;
+                n_walked += (unsigned long long)in_cube;
                 last = (long long)wbest;
             }
         }
@@ -492,7 +590,10 @@ __global__ void __launch_bounds__(kWarps * 32) knn_pca_kernel(const float4 *__re
             }
             __syncwarp();
         }
-        if (stats && lane == 0) atomicAdd(&stats[0], (unsigned long long)n_ranges);
+        if (stats && lane == 0) {
+            atomicAdd(&stats[0], n_walks);
+            atomicAdd(&stats[1], n_walked);
+        }
     }
 }
 
@@ -529,8 +630,8 @@ using namespace gsl;
 extern "C" size_t gsl_region_workspace_bytes(int64_t N) { return rg::plan(N).total; }
 
 extern "C" int gsl_region_knn_pca(const float *pos, int64_t N, int k, const double *normals_in, double *normals,
-                                  double *residuals, double *centroids, int32_t *knn, void *ws, size_t ws_bytes,
-                                  void *stream)
+                                  double *residuals, double *centroids, int32_t *knn, unsigned long long *stats,
+                                  void *ws, size_t ws_bytes, void *stream)
 {
     if (N < 0 || k < 1 || (N > 0 && (!pos || !ws))) return fail(GSL_EINVAL, "gsl_region_knn_pca: bad argument");
     if (N > 0x7fffffffLL) return fail(GSL_EINVAL, "gsl_region_knn_pca: more than 2^31 - 1 points");
@@ -550,7 +651,7 @@ extern "C" int gsl_region_knn_pca(const float *pos, int64_t N, int k, const doub
     const int grid = (int)std::min<int64_t>((N + 255) / 256, 1024);
     rg::bbox_kernel<<<grid, 256, 0, st>>>(pos, N, bbox);
     GSL_LAUNCH_CHECK("rg::bbox_kernel");
-    rg::bbox_final_kernel<<<1, 32, 0, st>>>(bbox, grid, ginfo);
+    rg::bbox_final_kernel<<<1, 256, 0, st>>>(bbox, grid, ginfo);
     GSL_LAUNCH_CHECK("rg::bbox_final_kernel");
     const int wide = (int)std::min<int64_t>((N + 255) / 256, (int64_t)sm_count() * 8);
     rg::cell_key_kernel<<<wide, 256, 0, st>>>(pos, N, ginfo, keys_a);
@@ -577,7 +678,7 @@ extern "C" int gsl_region_knn_pca(const float *pos, int64_t N, int k, const doub
     const size_t smem = sizeof(rg::WarpScratch) * rg::kWarps;
     GSL_CUDA_TRY(cudaFuncSetAttribute(rg::knn_pca_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int qgrid = (int)std::min<int64_t>((N + rg::kWarps - 1) / rg::kWarps, (int64_t)sm_count() * 16);
-    rg::knn_pca_kernel<<<qgrid, rg::kWarps * 32, smem, st>>>(sorted, N, k, ginfo, T, out, nullptr);
+    rg::knn_pca_kernel<<<qgrid, rg::kWarps * 32, smem, st>>>(sorted, N, k, ginfo, T, out, stats);
     GSL_LAUNCH_CHECK("rg::knn_pca_kernel");
     return GSL_OK;
 }

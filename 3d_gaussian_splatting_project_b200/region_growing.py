@@ -36,7 +36,7 @@ def _device_points(V1) -> torch.Tensor:
 
 
 def knn_pca(V1, k: int, normals_in=None, want_normals=True, want_residuals=True, want_centroids=False,
-            want_knn=False) -> dict:
+            want_knn=False, want_stats=False) -> dict:
     """One pass of gsl_region_knn_pca.  Returns device tensors: normals f64 [N,3], residuals f64 [N],
     centroids f64 [N,3], knn int32 [N,k] (k <= 64), as requested."""
     pos = _device_points(V1)
@@ -57,12 +57,14 @@ def knn_pca(V1, k: int, normals_in=None, want_normals=True, want_residuals=True,
         out["centroids"] = torch.empty((N, 3), dtype=torch.float64, device=dev)
     if want_knn:
         out["knn"] = torch.empty((N, int(k)), dtype=torch.int32, device=dev)
+    if want_stats:          # [walks over candidate cells, points visited]: work counters
+        out["stats"] = torch.zeros(2, dtype=torch.int64, device=dev)
     L = lib()
     ws = ops._ws.get(dev, L.gsl_region_workspace_bytes(N))
     ptr = lambda name: out[name].data_ptr() if name in out else None
     with torch.cuda.device(dev):
         check(L.gsl_region_knn_pca(pos.data_ptr(), N, int(k), nin.data_ptr() if nin is not None else None, ptr("normals"),
-                                   ptr("residuals"), ptr("centroids"), ptr("knn"), ws.data_ptr(), ws.numel(), ops._stream()))
+                                   ptr("residuals"), ptr("centroids"), ptr("knn"), ptr("stats"), ws.data_ptr(), ws.numel(), ops._stream()))
     return out
 
 

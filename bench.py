@@ -242,7 +242,9 @@ def next_rows(a, gs, orc, pos, labels_host, dev):
     if m >= k:
         sub = dpos[:m].contiguous()
         res, ms = timed(lambda: rgrow.knn_pca(sub, k), 2)
+        st = rgrow.knn_pca(sub, k, want_stats=True)["stats"].cpu().numpy()
         row = {"points": m, "k": k, "ms": ms, "points_per_s": m / (ms * 1e-3),
+               "walks_per_query": float(st[0]) / m, "points_visited_per_neighbour_found": float(st[1]) / (m * k),
                "note": "normals + residuals of region_growing.py compute_normals / compute_residuals (k = 2000 as in its __main__)"}
         if orc is not None:
             q0, q1 = m // 2, m // 2 + 200
