@@ -343,7 +343,7 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
-__global__ void __launch_bounds__(kWarps * 32, 2) knn_pca_kernel(const float4 *__restrict__ sorted, int64_t N, int k,
+__global__ void __launch_bounds__(kWarps * 32, 3) knn_pca_kernel(const float4 *__restrict__ sorted, int64_t N, int k,
                                                               const GridInfo *__restrict__ ginfo, Tables T, QueryOut out,
                                                               unsigned long long *__restrict__ stats)
 {
