@@ -72,6 +72,12 @@ __global__ void __launch_bounds__(256) viewer_depth_kernel(const float *__restri
     }
 }
 
+__global__ void viewer_init_kernel(int *__restrict__ minmax)
+{
+    minmax[0] = INT_MAX;
+    minmax[1] = INT_MIN;
+}
+
 // gs:443-447: bucket = ((depth - minDepth) * depthInv) | 0 with depthInv = 65536 / (max - min).
 // The result lies in [0, 65536]; 65536 (the deepest Gaussians, when the product does not round
 // below it) indexes past the reference's 65536-entry typed arrays -- see viewer_depth_sort.
@@ -247,8 +253,8 @@ extern "C" int gsl_viewer_depth_sort(const float *pos, int64_t N, int stride, co
     int32_t *keys_a = (int32_t *)(w + p.keys_a);
     uint32_t *keys_b = (uint32_t *)(w + p.keys_b), *idx_a = (uint32_t *)(w + p.idx_a), *hist = (uint32_t *)(w + p.hist);
     int *minmax = (int *)(w + p.minmax);
-    const int init[2] = {INT_MAX, INT_MIN};
-    GSL_CUDA_TRY(cudaMemcpyAsync(minmax, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    viewer_init_kernel<<<1, 1, 0, st>>>(minmax);          // (a copy from host memory would synchronise the stream)
+    GSL_LAUNCH_CHECK("viewer_init_kernel");
     const int grid = (int)std::min<int64_t>((N + 255) / 256, (int64_t)sm_count() * 8);
     viewer_depth_kernel<<<grid, 256, 0, st>>>(pos, N, stride, view_proj[2], view_proj[6], view_proj[10], keys_a, minmax);
     GSL_LAUNCH_CHECK("viewer_depth_kernel");
