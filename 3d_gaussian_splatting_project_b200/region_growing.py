@@ -1,6 +1,7 @@
 """Drop-in for the numerical part of the reference's 3D_clustering/region_growing.py (`rg`;
 SURVEY.md section 8f, N4): same function names, arguments, prints and return types.
 
+    get_vertex_info / get_pos / generate_sphere_ply / set_clusters / set_normal    rg:11-76, :224-261 (PLY helpers)
     compute_normals(V1, k)                   rg:78-127   -> float64 [N, 3]
     compute_residuals(V1, normals, k)        rg:130-163  -> float64 [N]
     segmentation_3D(points, normals, residuals, residual_threshold, angle_threshold, k)   rg:166-221
@@ -13,10 +14,13 @@ GPU produced.  There is no CPU path for the numerical part.
 """
 from __future__ import annotations
 
+import math
+import random
+
 import numpy as np
 import torch
 
-from . import ops
+from . import ops, plyio
 from ._native import check, lib
 
 
@@ -107,3 +111,85 @@ def segmentation_3D(points, normals, residuals, residual_threshold, angle_thresh
     regions = [order[bounds[i]:bounds[i + 1]].tolist() for i in range(int(r))]
     regions.sort(key=len, reverse=True)             # rg:219 (stable, like list.sort)
     return regions
+
+
+# --------------------------------------------------------------------------------------
+# PLY helpers of the script (host side; plyfile is replaced by plyio)
+# --------------------------------------------------------------------------------------
+def get_vertex_info(plydata):
+    """(points [N,3], colors [N,3]) = (x, y, z), (f_dc_0..2) of the vertex element (rg:11-30)."""
+    vertices = plydata["vertex"]
+    points = np.column_stack((vertices["x"], vertices["y"], vertices["z"]))
+    colors = np.column_stack((vertices["f_dc_0"], vertices["f_dc_1"], vertices["f_dc_2"]))
+    return points, colors
+
+
+def get_pos(plydata):
+    """Positions [N,3] of the vertex element (rg:32-40; the reference reads the global `plydata`)."""
+    vertices = plydata["vertex"]
+    return np.column_stack((vertices["x"], vertices["y"], vertices["z"]))
+
+
+def generate_sphere_ply(radius=1.0, subdivisions=50, filename="sphere.ply"):
+    """ASCII PLY of a red latitude / longitude sphere (rg:42-76), same text byte for byte."""
+    vertices = []
+    for i in range(subdivisions + 1):
+        theta = i * math.pi / subdivisions
+        for j in range(subdivisions):
+            phi = j * 2.0 * math.pi / subdivisions
+            vertices.append([radius * math.sin(theta) * math.cos(phi), radius * math.sin(theta) * math.sin(phi),
+                             radius * math.cos(theta), 255, 0, 0])
+    vertices = np.array(vertices)
+    with open(filename, "w") as ply_file:
+        ply_file.write("ply\nformat ascii 1.0\n")
+        ply_file.write(f"element vertex {len(vertices)}\n")
+        ply_file.write("property float x\nproperty float y\nproperty float z\n")
+        ply_file.write("property uchar red\nproperty uchar green\nproperty uchar blue\nend_header\n")
+        for v in vertices:
+            ply_file.write(f"{v[0]:.6f} {v[1]:.6f} {v[2]:.6f} {int(v[3])} {int(v[4])} {int(v[5])}\n")
+    print(f"Sphere saved to {filename}")
+
+
+def set_clusters(plydata, R, modified_path):
+    """One random colour per region into f_dc_0..2, then write the PLY in the input's format (rg:224-241)."""
+    vertices = plydata["vertex"]
+    for Rc in R:
+        r = np.array(Rc)
+        vertices["f_dc_0"][r] = random.random()
+        vertices["f_dc_1"][r] = random.random()
+        vertices["f_dc_2"][r] = random.random()
+    with open(modified_path, "wb") as f:
+        print("writing new data")
+        plydata.write(f)
+
+
+def set_normal(plydata, normals, modified_path):
+    """Normals into the diffuse colour channels, then write the PLY (rg:244-261)."""
+    vertices = plydata["vertex"]
+    vertices["f_dc_0"] = normals[:, 0]
+    vertices["f_dc_1"] = normals[:, 1]
+    vertices["f_dc_2"] = normals[:, 2]
+    print(normals[:, 0] * 255)
+    with open(modified_path, "wb") as f:
+        print("writing new data")
+        plydata.write(f)
+
+
+def main(file_path=r"data\point_cloud.ply", modified_path=r"3D_clustering\clustering.ply"):
+    """The script's __main__ (rg:263-285) with its constants: k = 2000 for normals and residuals,
+    residual_threshold 0.1, angle_threshold 0.05, k = 10 for the growth."""
+    with open(file_path, "rb") as f:
+        plydata = plyio.read_ply(f)
+    points = get_pos(plydata)
+    normals = compute_normals(points, 2000)
+    residuals = compute_residuals(points, normals, 2000)
+    print(residuals)
+    R = segmentation_3D(points, normals, residuals, residual_threshold=0.1, angle_threshold=0.05, k=10)
+    print(f"number of segments: {len(R)}")
+    set_clusters(plydata, R, modified_path)
+    return R
+
+
+if __name__ == "__main__":
+    import sys
+    main(*sys.argv[1:3])

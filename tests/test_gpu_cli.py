@@ -78,3 +78,38 @@ def test_lifting_script_c2(oracle, tmp_path):
     assert f"Total gaussians: {len(pos)}" in out.stdout
     n_unseen = int((want == -1).sum())
     assert f"Label -1: {n_unseen} gaussians" in out.stdout
+
+
+def test_region_growing_script(oracle, tmp_path):
+    """python 3D_clustering/region_growing.py in.ply out.ply: the script's __main__ flow (rg:263-285:
+    normals and residuals with k = 2000, growth with k = 10) on a 6000-vertex stand-in; the regions
+    written as colours equal the ones the oracle grows from the oracle's own normals / residuals."""
+    plyio = pkg("plyio")
+    src, dst = tmp_path / "point_cloud.ply", tmp_path / "clustering.ply"
+    v = _standin_ply(src, 6000, seed=3)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "3D_clustering", "region_growing.py"), str(src), str(dst)],
+                         capture_output=True, text=True, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = out.stdout.splitlines()
+    assert lines[0] == "Calculating normals..." and "Calculating residuals..." in lines and lines[-1] == "writing new data"
+    n_segments = int([ln for ln in lines if ln.startswith("number of segments: ")][0].split(": ")[1])
+    back = plyio.read_ply(dst)
+    assert not back.text and back["vertex"].data.dtype == v.dtype
+    for name in ("x", "y", "z", "opacity", "rot_3"):
+        assert np.array_equal(back["vertex"][name], v[name])
+    # every region got one random colour triple: vertices with equal triples form the regions
+    colour = np.stack([back["vertex"][f"f_dc_{i}"] for i in range(3)], 1)
+    _, region_written = np.unique(colour, axis=0, return_inverse=True)
+    pos = np.column_stack((v["x"], v["y"], v["z"])).astype(np.float32)
+    ref = oracle.region_knn_pca(pos, 2000)
+    knn = oracle.region_knn_pca(pos, 10, want_knn=True)["knn"]
+    region_ref, n_ref = oracle.region_grow(knn, ref["normals"], ref["residuals"], 0.1, 0.05)
+    # the GPU's normals differ from the oracle's in the last bits, which can move a borderline smoothness
+    # test (|cos| vs cos 0.05): allow a handful of points to change region
+    assert abs(n_segments - n_ref) <= max(3, n_ref // 100)
+    pairs = {}
+    for a, b in zip(region_written.reshape(-1).tolist(), region_ref.tolist()):
+        pairs.setdefault(a, {}).setdefault(b, 0)
+        pairs[a][b] += 1
+    agree = sum(max(d.values()) for d in pairs.values())
+    assert agree >= 0.98 * len(pos)

@@ -68,6 +68,41 @@ def test_dropin_surfaces_match_reference_signatures():
     assert len(km.COLORS) == 8 and km.COLORS[3] == [126, 24, 145]
 
 
+def test_region_growing_and_viewer_surfaces_match_reference():
+    """Names and parameters of 3D_clustering/region_growing.py (rg:11-261) and of the viewer worker's
+    functions (gaussians_selection.js:110, :361, :417), snake case for the latter."""
+    rg, viewer = pkg("region_growing"), pkg("viewer")
+    want = {"get_vertex_info": ["plydata"], "generate_sphere_ply": ["radius", "subdivisions", "filename"],
+            "compute_normals": ["V1", "k"], "compute_residuals": ["V1", "normals", "k"],
+            "segmentation_3D": ["points", "normals", "residuals", "residual_threshold", "angle_threshold", "k"],
+            "set_clusters": ["plydata", "R", "modified_path"]}
+    for name, params in want.items():
+        assert list(inspect.signature(getattr(rg, name)).parameters) == params, name
+    sp = inspect.signature(rg.generate_sphere_ply).parameters
+    assert (sp["radius"].default, sp["subdivisions"].default, sp["filename"].default) == (1.0, 50, "sphere.ply")
+    assert list(inspect.signature(viewer.perform_hit_testing).parameters)[:5] == ["x", "y", "view_matrix", "projection_matrix", "viewport"]
+    assert list(inspect.signature(viewer.run_sort).parameters)[:2] == ["positions", "view_proj"]
+    assert viewer.NO_SELECTION == -999999
+    # multiply4 is plain host arithmetic: column-major product in the worker's association order
+    a = [float(i) for i in range(1, 17)]
+    ident = [1.0 if i % 5 == 0 else 0.0 for i in range(16)]
+    assert viewer.multiply4(a, ident) == a and viewer.multiply4(ident, a) == a
+
+
+def test_generate_sphere_ply_text(tmp_path, capsys):
+    """rg:42-76: header and the '%.6f %.6f %.6f 255 0 0' rows, (subdivisions + 1) * subdivisions vertices."""
+    rg = pkg("region_growing")
+    path = tmp_path / "s.ply"
+    rg.generate_sphere_ply(radius=2.0, subdivisions=4, filename=str(path))
+    assert capsys.readouterr().out == f"Sphere saved to {path}\n"
+    lines = path.read_text().split("\n")
+    assert lines[:10] == ["ply", "format ascii 1.0", "element vertex 20", "property float x", "property float y", "property float z",
+                          "property uchar red", "property uchar green", "property uchar blue", "end_header"]
+    assert lines[10] == "0.000000 0.000000 2.000000 255 0 0"                 # theta = 0: the pole
+    assert lines[10 + 8] == "2.000000 0.000000 0.000000 255 0 0"             # theta = pi/2, phi = 0
+    assert len(lines) == 10 + 20 + 1 and lines[-1] == ""
+
+
 def test_project_gaussian_scalar_matches_oracle(oracle):
     dls = pkg("deep_learning_segmentation")
     c = load_lift_case("lift_lookat_fullres")
