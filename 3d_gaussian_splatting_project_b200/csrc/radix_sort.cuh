@@ -7,6 +7,8 @@
 //   ranking  = in a round, __match_any_sync groups the lanes holding the same digit; a lane's
 //              rank is the per-warp running count of its digit plus the number of lower lanes
 //              of its group -- no atomics, and the rank order is the input order (stability).
+//   scatter  = through shared memory: the tile is put in sorted order there and written out by
+//              consecutive threads, so runs of one digit leave as contiguous stores.
 //   bases    = hist[digit][tile]: one CTA per digit scans its row and adds the number of pairs with
 //              a smaller digit (digit totals are accumulated by the histogram kernel).
 //
@@ -46,17 +48,28 @@ __device__ __forceinline__ void rank_warp_run(const uint32_t *__restrict__ keys,
 {
     constexpr uint32_t DIG = 1u << BITS;
     const unsigned lane = threadIdx.x & 31u, lt = lanemask_lt();
+    // all loads first: the ranking rounds below are separated by warp barriers, which would otherwise
+    // put one memory round trip in front of every round
+#pragma unroll
+    for (int r = 0; r < kItems; ++r) {
+        const int64_t i = warp_begin + r * 32 + lane;
+        key[r] = i < N ? keys[i] : 0u;
+    }
 #pragma unroll
     for (int r = 0; r < kItems; ++r) {
         const int64_t i = warp_begin + r * 32 + lane;
         const bool valid = i < N;
         const unsigned act = __ballot_sync(0xffffffffu, valid);
-        key[r] = 0;
         rank[r] = 0;
         if (valid) {
-            key[r] = keys[i];
             const uint32_t d = (key[r] >> shift) & (DIG - 1u);
-            const unsigned peers = __match_any_sync(act, d);
+            // lanes holding the same digit: one ballot per digit bit (measured faster than match.any here)
+            unsigned peers = act;
+#pragma unroll
+            for (int b = 0; b < BITS; ++b) {
+                const unsigned bal = __ballot_sync(act, (d >> b) & 1u);
+                peers &= ((d >> b) & 1u) ? bal : ~bal;
+            }
             const uint32_t pre = cnt_warp[d];
             __syncwarp(act);
             if ((peers & lt) == 0) cnt_warp[d] = pre + __popc(peers);
@@ -138,6 +151,22 @@ __global__ void __launch_bounds__(256) scan_rows_kernel(uint32_t *__restrict__ h
 // means the payload is the pair's own position (first pass of an index sort).  A pair whose FULL
 // key equals drop_key gets `drop_payload` instead of its payload (viewer.cu: the typed-array
 // out-of-range quirk of the reference's counting sort); pass 0xffffffff to disable.
+//
+// The tile's pairs are first put in sorted order in shared memory (position = first slot of the
+// digit in the tile + pairs of that digit in lower warps + rank inside the warp) and then written
+// out by consecutive threads: a digit's run inside a tile is contiguous in the output, so a warp's
+// store covers a few sectors instead of one per lane.
+template <int BITS>
+struct ScatterSmem {
+    static constexpr int DIG = 1 << BITS;
+    uint32_t cnt[kWarps][DIG];      // per-warp digit counts, then pairs of the digit in lower warps
+    uint32_t lstart[DIG];           // first slot of the digit in the tile's sorted order
+    uint32_t gdelta[DIG];           // output position of that slot - lstart
+    uint32_t wsum[kWarps];
+    uint32_t key[kTile];
+    uint32_t pay[kTile];
+};
+
 template <int BITS>
 __global__ void __launch_bounds__(kThreads) scatter_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ pay_in,
                                                            uint32_t *__restrict__ keys_out, uint32_t *__restrict__ pay_out,
@@ -145,23 +174,44 @@ __global__ void __launch_bounds__(kThreads) scatter_kernel(const uint32_t *__res
                                                            uint32_t drop_key, uint32_t drop_payload)
 {
     constexpr int DIG = 1 << BITS;
-    __shared__ uint32_t cnt[kWarps][DIG];
-    for (int d = threadIdx.x; d < kWarps * DIG; d += kThreads) (&cnt[0][0])[d] = 0;
+    static_assert(DIG <= kThreads, "one thread per digit");
+    extern __shared__ __align__(16) unsigned char radix_smem[];
+    ScatterSmem<BITS> &S = *reinterpret_cast<ScatterSmem<BITS> *>(radix_smem);
+    for (int d = threadIdx.x; d < kWarps * DIG; d += kThreads) (&S.cnt[0][0])[d] = 0;
     __syncthreads();
     const int tile = blockIdx.x;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const int64_t warp_begin = (int64_t)tile * kTile + (int64_t)warp * 32 * kItems;
+    const int64_t tile_begin = (int64_t)tile * kTile;
+    const int64_t warp_begin = tile_begin + (int64_t)warp * 32 * kItems;
+    const int tile_n = (int)(N - tile_begin < kTile ? N - tile_begin : kTile);
     uint32_t key[kItems], rank[kItems];
-    rank_warp_run<BITS>(keys, N, warp_begin, shift, cnt[warp], key, rank);
+    rank_warp_run<BITS>(keys, N, warp_begin, shift, S.cnt[warp], key, rank);
     __syncthreads();
-    for (int d = threadIdx.x; d < DIG; d += kThreads) {
-        uint32_t run = base[(size_t)d * tiles + tile];
+    // thread d: pairs of digit d in the tile, and per warp the pairs in lower warps
+    uint32_t mine = 0;
+    if (threadIdx.x < DIG) {
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) {
-            const uint32_t c = cnt[w][d];
-            cnt[w][d] = run;
-            run += c;
+            const uint32_t c = S.cnt[w][threadIdx.x];
+            S.cnt[w][threadIdx.x] = mine;
+            mine += c;
         }
+    }
+    // exclusive scan of `mine` over the digits (one per thread)
+    uint32_t inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (unsigned)o) inc += t;
+    }
+    if (lane == 31) S.wsum[warp] = inc;
+    __syncthreads();
+    if (threadIdx.x < DIG) {
+        uint32_t before = 0;
+        for (unsigned w = 0; w < warp; ++w) before += S.wsum[w];
+        const uint32_t ls = before + inc - mine;
+        S.lstart[threadIdx.x] = ls;
+        S.gdelta[threadIdx.x] = base[(size_t)threadIdx.x * tiles + tile] - ls;
     }
     __syncthreads();
 #pragma unroll
@@ -169,14 +219,21 @@ __global__ void __launch_bounds__(kThreads) scatter_kernel(const uint32_t *__res
         const int64_t i = warp_begin + r * 32 + lane;
         if (i < N) {
             const uint32_t d = (key[r] >> shift) & (uint32_t)(DIG - 1);
-            const uint32_t at = cnt[warp][d] + rank[r];
-            if (keys_out) keys_out[at] = key[r];
+            const uint32_t at = S.lstart[d] + S.cnt[warp][d] + rank[r];
+            S.key[at] = key[r];
             if (pay_out) {
                 uint32_t p = pay_in ? pay_in[i] : (uint32_t)i;
                 if (key[r] == drop_key) p = drop_payload;
-                pay_out[at] = p;
+                S.pay[at] = p;
             }
         }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < tile_n; i += kThreads) {
+        const uint32_t k = S.key[i];
+        const uint32_t at = S.gdelta[(k >> shift) & (uint32_t)(DIG - 1)] + (uint32_t)i;
+        if (keys_out) keys_out[at] = k;
+        if (pay_out) pay_out[at] = S.pay[i];
     }
 }
 
@@ -193,8 +250,9 @@ inline int pass(const uint32_t *keys, const uint32_t *pay_in, uint32_t *keys_out
     GSL_LAUNCH_CHECK("radix::histogram_kernel");
     scan_rows_kernel<BITS><<<1 << BITS, 256, 0, st>>>(hist, total, tiles);
     GSL_LAUNCH_CHECK("radix::scan_rows_kernel");
-    scatter_kernel<BITS><<<tiles, kThreads, 0, st>>>(keys, pay_in, keys_out, pay_out, N, shift, hist, tiles, drop_key,
-                                                     drop_payload);
+    GSL_CUDA_TRY(cudaFuncSetAttribute(scatter_kernel<BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem<BITS>)));
+    scatter_kernel<BITS><<<tiles, kThreads, sizeof(ScatterSmem<BITS>), st>>>(keys, pay_in, keys_out, pay_out, N, shift, hist, tiles,
+                                                                             drop_key, drop_payload);
     GSL_LAUNCH_CHECK("radix::scatter_kernel");
     return GSL_OK;
 }

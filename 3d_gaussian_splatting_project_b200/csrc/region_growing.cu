@@ -373,14 +373,13 @@ __global__ void __launch_bounds__(kWarps * 32, 3) knn_pca_kernel(const float4 *_
 
         // 1. the finest cube that provably holds the k nearest neighbours; the counting walk also fills the
         //    histogram of the leading digit
-        int n_ranges = 0;
         int64_t in_cube = 0;
         double R2 = CUDART_INF;
         bool have_hist = false;
         for (int L = kLevels; L >= 0; --L) {
             bool found = false;
             for (int ring = (L == kLevels ? 1 : 2); ring <= 3; ++ring) {
-                n_ranges = build_ranges(T, N, L, ring, c7x >> (kLevels - L), c7y >> (kLevels - L), c7z >> (kLevels - L), sc, lane,
+                build_ranges(T, N, L, ring, c7x >> (kLevels - L), c7y >> (kLevels - L), c7z >> (kLevels - L), sc, lane,
                                         &in_cube);
                 if (L == 0) {
                     R2 = CUDART_INF;
