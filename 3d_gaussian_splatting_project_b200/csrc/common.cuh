@@ -38,7 +38,7 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 int sm_count();
 
 // kmeans_ordered.cu: scratch for gsl_kmeans_update_ordered.
-size_t ordered_workspace_bytes(int64_t N, int K);
+size_t ordered_workspace_bytes(int64_t N, int D, int K);
 
 // kmeans_tc.cu: tensor-core screened assignment (K <= 64, 8 <= D <= 64).
 bool tc_supported(int D, int K);

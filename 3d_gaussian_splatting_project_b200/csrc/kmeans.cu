@@ -369,7 +369,7 @@ extern "C" size_t gsl_kmeans_workspace_bytes(int64_t N, int D, int K)
     if (N < 0 || D < 1 || K < 1) return 0;
     const size_t parts = (size_t)sm_count() * 2;
     const size_t step = parts * (size_t)K * (D + 1) * sizeof(double) + 256;
-    const size_t ord = ordered_workspace_bytes(N, K);
+    const size_t ord = ordered_workspace_bytes(N, D, K);
     return step > ord ? step : ord;
 }
 

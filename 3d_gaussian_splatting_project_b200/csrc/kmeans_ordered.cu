@@ -11,17 +11,23 @@
 //   ordered_start_kernel     exclusive scan of the totals -> segment starts
 //   ordered_scatter_kernel   stable scatter of row indices into per-cluster member lists
 //                            (warp match_any ranks keep ascending row order)
-//   ordered_chain_kernel     CTA per (cluster, 32 dims): seven producer warps cp.async member rows
-//                            into a 4-deep shared-memory ring while warp 0 adds them in
-//                            order, lane = dimension.  (Round 2 tried one CTA per cluster with an
-//                            mbarrier-advanced ring, consumers never at a block barrier: 12.5 ms
-//                            against 4.5 ms for this kernel at 6 M x 59 -- two dependent DRAM round
-//                            trips per batch and warp, index then rows; reverted.)
+//   ordered_gather_kernel    member rows in list order into a contiguous, padded array per 32-dim chunk
+//   ordered_stream_kernel    one warp per (cluster, 32 dims): TMA bulk copies of its contiguous rows into
+//                            a shared-memory ring, added in order, lane = dimension (the default)
+//   ordered_chain_kernel     the round-1 form (GSLIFT_ORDERED_STREAM=0): CTA per (cluster, 32 dims), seven
+//                            producer warps cp.async member rows into a 4-deep shared-memory ring while
+//                            warp 0 adds them in order.  (Round 2 also tried one CTA per cluster with an
+//                            mbarrier-advanced ring fed by per-row cp.async: 12.5 ms against 4.5 ms.)
 //   shift_kernel             ||new - old||_F
 //
 // This is the parity mode (single device).  The throughput mode is gsl_kmeans_step's float64
 // segmented reduction, which is sharded and all-reduced.
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "common.cuh"
+#include "kmeans_screen.cuh"
 
 namespace gsl {
 
@@ -45,10 +51,10 @@ ordered_count_kernel(const int32_t *__restrict__ labels, int64_t N, int K, int32
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < K; i += kOrdThreads) tile_counts[(size_t)blockIdx.x * K + i] = hist[i];
+    for (int i = threadIdx.x; i < K; i += kOrdThreads) tile_counts[(size_t)i * gridDim.x + blockIdx.x] = hist[i];      // [K][n_tiles]: the scan reads a cluster's row contiguously
 }
 
-// Block k: tile_counts[:, k] -> exclusive offsets in place, total[k].
+// Block k: tile_counts[k][:] -> exclusive offsets in place, total[k].
 __global__ void __launch_bounds__(kOrdThreads)
 ordered_scan_kernel(int32_t *__restrict__ tile_counts, int n_tiles, int K, int64_t *__restrict__ total)
 {
@@ -57,7 +63,7 @@ ordered_scan_kernel(int32_t *__restrict__ tile_counts, int n_tiles, int K, int64
     const int seg = (n_tiles + kOrdThreads - 1) / kOrdThreads;
     const int lo = min(t * seg, n_tiles), hi = min(lo + seg, n_tiles);
     int64_t s = 0;
-    for (int i = lo; i < hi; ++i) s += tile_counts[(size_t)i * K + k];
+    for (int i = lo; i < hi; ++i) s += tile_counts[(size_t)k * n_tiles + i];
     part[t] = s;
     __syncthreads();
     if (t == 0) {
@@ -68,17 +74,26 @@ ordered_scan_kernel(int32_t *__restrict__ tile_counts, int n_tiles, int K, int64
     __syncthreads();
     int64_t run = part[t];
     for (int i = lo; i < hi; ++i) {
-        const int c = tile_counts[(size_t)i * K + k];
-        tile_counts[(size_t)i * K + k] = (int32_t)run;   // within-cluster offset (< N < 2^31)
+        const int c = tile_counts[(size_t)k * n_tiles + i];
+        tile_counts[(size_t)k * n_tiles + i] = (int32_t)run;   // within-cluster offset (< N < 2^31)
         run += c;
     }
 }
 
-__global__ void ordered_start_kernel(const int64_t *__restrict__ total, int K, int64_t *__restrict__ start)
+// start[k] = members before cluster k; pstart[k] = the same with every cluster padded to a multiple of four
+// rows (pstart[K] = padded total): the streamed chain reads its rows in groups of four.
+__global__ void ordered_start_kernel(const int64_t *__restrict__ total, int K, int64_t *__restrict__ start,
+                                     int64_t *__restrict__ pstart)
 {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
-        int64_t run = 0;
-        for (int k = 0; k < K; ++k) { start[k] = run; run += total[k]; }
+        int64_t run = 0, prun = 0;
+        for (int k = 0; k < K; ++k) {
+            start[k] = run;
+            pstart[k] = prun;
+            run += total[k];
+            prun += (total[k] + 3) & ~(int64_t)3;
+        }
+        pstart[K] = prun;
     }
 }
 
@@ -103,7 +118,7 @@ ordered_scatter_kernel(const int32_t *__restrict__ labels, int64_t N, int K,
     }
     __syncthreads();
     for (int k = t; k < K; k += kOrdThreads) {
-        int64_t run = start[k] + tile_offsets[(size_t)blockIdx.x * K + k];
+        int64_t run = start[k] + tile_offsets[(size_t)k * gridDim.x + blockIdx.x];
         for (int ww = 0; ww < 8; ++ww) { base[ww * K + k] = run; run += wc[ww * K + k]; }
     }
     __syncthreads();
@@ -229,6 +244,131 @@ ordered_chain_kernel(const float *__restrict__ data, int D, const int32_t *__res
     if (w == 0 && live) new_c[(size_t)k * D + d] = (float)((double)acc / (double)n);
 }
 
+// ---- streamed form of the chain (default) --------------------------------------------------------
+// The chain kernel above has to collect its member rows with one 4-byte cp.async per lane and row
+// (rows of D = 59 floats are only 4-byte aligned), and ncu shows that this is what paces it: 224
+// such instructions per batch and SM, ~2750 cycles per batch against ~900 for the 224 dependent
+// adds.  Splitting the work removes the gather from the serial part:
+//   ordered_gather_kernel   fully parallel and bandwidth bound: member rows in list order into a
+//                           contiguous array per 32-dimension chunk (128 bytes per row and chunk,
+//                           zero padded; layout below)
+//   ordered_stream_kernel   one WARP per (cluster, chunk): its rows are one contiguous, 16-byte
+//                           aligned stream, fetched by TMA bulk copies of 256 rows (one instruction
+//                           per 32 KB, completion on an mbarrier) four stages ahead, and added in
+//                           order, lane = dimension.  No other warp, no block barrier.
+constexpr int kStreamRows = 512;       // rows per stage (64 KB)
+constexpr int kStreamStages = 3;
+
+// rows32[chunk][group][lane][4]: the rows of a cluster start at a multiple of four slots (pstart), four
+// consecutive rows form a group, and a lane's four values of a group are contiguous -- the stream kernel
+// fetches them with one 16-byte shared load.  One warp per group: four member rows read lane = dimension,
+// one coalesced 512-byte store per chunk.
+__global__ void __launch_bounds__(256)
+ordered_gather_kernel(const float *__restrict__ data, int D, int n_chunks, const int32_t *__restrict__ members,
+                      const int64_t *__restrict__ start, const int64_t *__restrict__ pstart, const int64_t *__restrict__ total,
+                      int K, int64_t slots_pad, float *__restrict__ rows32)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t n_groups = pstart[K] >> 2;
+    for (int64_t g = warp; g < n_groups; g += n_warps) {
+        const int64_t slot = g << 2;
+        int lo = 0, hi = K - 1;                              // the cluster whose padded range holds the group
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (pstart[mid] <= slot) lo = mid;
+            else hi = mid - 1;
+        }
+        const int64_t m = slot - pstart[lo], n = total[lo], s = start[lo] + m;
+        int row[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) row[j] = m + j < n ? __ldg(members + s + j) : -1;
+        for (int c = 0; c < n_chunks; ++c) {
+            const int d = c * 32 + lane;
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = (row[j] >= 0 && d < D) ? __ldg(data + (size_t)row[j] * D + d) : 0.f;
+            __stcs(reinterpret_cast<float4 *>(rows32 + ((size_t)c * slots_pad + (size_t)slot) * 32) + lane,
+                   make_float4(v[0], v[1], v[2], v[3]));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(32)
+ordered_stream_kernel(const float *__restrict__ rows32, int64_t slots_pad, int D, const int64_t *__restrict__ pstart,
+                      const int64_t *__restrict__ total, const float *__restrict__ old_c, float *__restrict__ new_c)
+{
+    extern __shared__ __align__(128) float sbuf[];           // [kStreamStages][kStreamRows / 4][32][4]
+    __shared__ __align__(8) unsigned long long bars[kStreamStages];
+    const int k = blockIdx.x, lane = threadIdx.x, d = blockIdx.y * 32 + lane;
+    const bool live = d < D;
+    const int64_t n = total[k];
+    if (n == 0) {
+        if (live) new_c[(size_t)k * D + d] = old_c[(size_t)k * D + d];   // km:126 else-branch
+        return;
+    }
+    const float *src = rows32 + ((size_t)blockIdx.y * slots_pad + (size_t)pstart[k]) * 32;
+    const int64_t n_batches = (n + kStreamRows - 1) / kStreamRows;
+    if (lane == 0)
+        for (int s = 0; s < kStreamStages; ++s) mbar_init(&bars[s], 1);
+    __syncwarp();
+    auto issue = [&](int64_t b) {                            // lane 0: the copy of batch b into its stage
+        if (lane == 0 && b < n_batches) {
+            const int64_t rows = (min((int64_t)kStreamRows, n - b * kStreamRows) + 3) & ~(int64_t)3;   // whole groups
+            bulk_load_tile(sbuf + (size_t)(b % kStreamStages) * kStreamRows * 32, src + (size_t)b * kStreamRows * 32,
+                           (unsigned)(rows * 128), &bars[b % kStreamStages]);
+        }
+    };
+    for (int b = 0; b < kStreamStages - 1; ++b) issue(b);
+    float acc = -0.0f;              // (-0) + x == x for every x: same as starting from the first row
+    for (int64_t b = 0; b < n_batches; ++b) {
+        __syncwarp();               // every lane is done reading batch b - 1, whose stage is refilled now
+        issue(b + kStreamStages - 1);
+        mbar_wait(&bars[b % kStreamStages], (unsigned)((b / kStreamStages) & 1));
+        const int cnt = (int)min((int64_t)kStreamRows, n - b * kStreamRows);
+        const float4 *grp = reinterpret_cast<const float4 *>(sbuf + (size_t)(b % kStreamStages) * kStreamRows * 32) + lane;
+        // One dependent chain of adds, 32 rows = 8 groups = 8 shared loads of 16 bytes at a time; two
+        // register sets alternate so that one is being loaded while the other is added.  Measured: 6.1
+        // cycles per add (2.2 ms for the 719 k members of the largest C5 cluster); FFMA x * 1 + acc in place
+        // of FADD, 256-row instead of 512-row stages and 6 instead of 3 stages all measured the same.
+        int i = 0;                                           // rows done
+        const int nb = cnt >> 5;                             // whole blocks of 32 rows
+        if (nb > 0) {
+            float4 x[8], y[8];
+            auto add8 = [&](const float4 (&v)[8]) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    acc = __fadd_rn(acc, v[j].x); acc = __fadd_rn(acc, v[j].y); acc = __fadd_rn(acc, v[j].z); acc = __fadd_rn(acc, v[j].w);
+                }
+            };
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = grp[j * 32];
+            int blk = 0;                                     // invariant: x holds block blk, not yet added
+            for (; blk + 2 <= nb; blk += 2) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) y[j] = grp[((blk + 1) * 8 + j) * 32];
+                add8(x);
+                if (blk + 2 < nb) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) x[j] = grp[((blk + 2) * 8 + j) * 32];
+                }
+                add8(y);
+            }
+            if (blk < nb) add8(x);
+            i = nb << 5;
+        }
+        for (; i < cnt; i += 4) {                            // remaining groups; the last one may be partial
+            const float4 v = grp[(i >> 2) * 32];
+            acc = __fadd_rn(acc, v.x);
+            if (i + 1 < cnt) acc = __fadd_rn(acc, v.y);
+            if (i + 2 < cnt) acc = __fadd_rn(acc, v.z);
+            if (i + 3 < cnt) acc = __fadd_rn(acc, v.w);
+        }
+    }
+    if (live) new_c[(size_t)k * D + d] = (float)((double)acc / (double)n);
+}
+
 __global__ void __launch_bounds__(256)
 shift_kernel(const float *__restrict__ a, const float *__restrict__ b, int n, float *__restrict__ shift,
              const int *__restrict__ bad_label)
@@ -249,9 +389,9 @@ shift_kernel(const float *__restrict__ a, const float *__restrict__ b, int n, fl
     }
 }
 
-struct OrdWs { size_t tile_counts, total, start, members, bytes; };
+struct OrdWs { size_t tile_counts, total, start, pstart, members, rows32, slots_pad, bytes; };
 
-static OrdWs ordered_layout(int64_t N, int K)
+static OrdWs ordered_layout(int64_t N, int D, int K)
 {
     OrdWs o;
     const size_t n_tiles = (size_t)((N + kOrdTile - 1) / kOrdTile);
@@ -259,12 +399,17 @@ static OrdWs ordered_layout(int64_t N, int K)
     o.tile_counts = off; off += align_up(n_tiles * K * sizeof(int32_t), 256);
     o.total = off;       off += align_up((size_t)K * sizeof(int64_t), 256);
     o.start = off;       off += align_up((size_t)K * sizeof(int64_t), 256);
+    o.pstart = off;      off += align_up((size_t)(K + 1) * sizeof(int64_t), 256);
     o.members = off;     off += align_up((size_t)N * sizeof(int32_t), 256);
+    // streamed form: the member rows per 32-dimension chunk, 128 bytes each (the TMA copies want 16-byte
+    // aligned sources; the slot count is padded so that every chunk starts on a 256-byte boundary)
+    o.slots_pad = align_up((size_t)(N > 0 ? N : 1) + 4 * (size_t)K, 4);      // every cluster padded to whole groups of four
+    o.rows32 = off;      off += align_up((size_t)((D + 31) / 32) * o.slots_pad * 32 * sizeof(float), 256);
     o.bytes = off;
     return o;
 }
 
-size_t ordered_workspace_bytes(int64_t N, int K) { return ordered_layout(N, K).bytes; }
+size_t ordered_workspace_bytes(int64_t N, int D, int K) { return ordered_layout(N, D, K).bytes; }
 
 }  // namespace gsl
 
@@ -279,12 +424,13 @@ extern "C" int gsl_kmeans_update_ordered(const float *data, const int32_t *label
     if (D < 1 || D > GSL_KMEANS_MAX_D || K < 1 || K > GSL_KMEANS_MAX_K) return fail(GSL_EINVAL, "gsl_kmeans_update_ordered: bad K/D");
     if (!old_centroids || !new_centroids || !shift) return fail(GSL_EINVAL, "gsl_kmeans_update_ordered: null pointer");
     if (N > 0 && (!data || !labels || !ws)) return fail(GSL_EINVAL, "gsl_kmeans_update_ordered: null pointer");
-    const OrdWs L = ordered_layout(N, K);
+    const OrdWs L = ordered_layout(N, D, K);
     if (ws_bytes < L.bytes) return fail(GSL_EWORKSPACE, "gsl_kmeans_update_ordered: workspace %zu < %zu", ws_bytes, L.bytes);
     unsigned char *base = reinterpret_cast<unsigned char *>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
     int32_t *tile_counts = reinterpret_cast<int32_t *>(base + L.tile_counts - 256);
     int64_t *total = reinterpret_cast<int64_t *>(base + L.total - 256);
     int64_t *start = reinterpret_cast<int64_t *>(base + L.start - 256);
+    int64_t *pstart = reinterpret_cast<int64_t *>(base + L.pstart - 256);
     int32_t *members = reinterpret_cast<int32_t *>(base + L.members - 256);
     const int n_tiles = (int)((N + kOrdTile - 1) / kOrdTile);
     int *bad_label = reinterpret_cast<int *>(base);          // first word of the workspace header
@@ -293,23 +439,39 @@ extern "C" int gsl_kmeans_update_ordered(const float *data, const int32_t *label
     if (N == 0) {
         GSL_CUDA_TRY(cudaMemsetAsync(total, 0, sizeof(int64_t) * (size_t)K, st));
         GSL_CUDA_TRY(cudaMemsetAsync(start, 0, sizeof(int64_t) * (size_t)K, st));
+        GSL_CUDA_TRY(cudaMemsetAsync(pstart, 0, sizeof(int64_t) * (size_t)(K + 1), st));
     } else {
         ordered_count_kernel<<<n_tiles, kOrdThreads, K * sizeof(int), st>>>(labels, N, K, tile_counts, bad_label);
         GSL_LAUNCH_CHECK("ordered_count_kernel");
         ordered_scan_kernel<<<K, kOrdThreads, 0, st>>>(tile_counts, n_tiles, K, total);
         GSL_LAUNCH_CHECK("ordered_scan_kernel");
-        ordered_start_kernel<<<1, 32, 0, st>>>(total, K, start);
+        ordered_start_kernel<<<1, 32, 0, st>>>(total, K, start, pstart);
         GSL_LAUNCH_CHECK("ordered_start_kernel");
         const size_t sc_smem = (size_t)(8 * K + ((8 * K) & 1)) * sizeof(int) + (size_t)8 * K * sizeof(int64_t);
         GSL_CUDA_TRY(cudaFuncSetAttribute(ordered_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));
         ordered_scatter_kernel<<<n_tiles, kOrdThreads, sc_smem, st>>>(labels, N, K, tile_counts, start, members);
         GSL_LAUNCH_CHECK("ordered_scatter_kernel");
     }
-    const size_t ch_smem = (size_t)kChainRing * kChainRows * 32 * sizeof(float);
-    GSL_CUDA_TRY(cudaFuncSetAttribute(ordered_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch_smem));
     dim3 grid((unsigned)K, (unsigned)((D + 31) / 32));
-    ordered_chain_kernel<<<grid, kOrdThreads, ch_smem, st>>>(data, D, members, start, total, old_centroids, new_centroids);
-    GSL_LAUNCH_CHECK("ordered_chain_kernel");
+    static const bool streamed = [] { const char *e = getenv("GSLIFT_ORDERED_STREAM"); return !(e && e[0] == '0'); }();
+    if (streamed) {
+        float *rows32 = reinterpret_cast<float *>(base + L.rows32 - 256);
+        if (N > 0) {
+            const int64_t warps = (N + 3) / 4 + K;
+            const unsigned g = (unsigned)std::min<int64_t>((warps * 32 + 255) / 256, (int64_t)sm_count() * 16);
+            ordered_gather_kernel<<<g, 256, 0, st>>>(data, D, (int)grid.y, members, start, pstart, total, K, (int64_t)L.slots_pad, rows32);
+            GSL_LAUNCH_CHECK("ordered_gather_kernel");
+        }
+        const size_t st_smem = (size_t)kStreamStages * kStreamRows * 32 * sizeof(float);
+        GSL_CUDA_TRY(cudaFuncSetAttribute(ordered_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st_smem));
+        ordered_stream_kernel<<<grid, 32, st_smem, st>>>(rows32, (int64_t)L.slots_pad, D, pstart, total, old_centroids, new_centroids);
+        GSL_LAUNCH_CHECK("ordered_stream_kernel");
+    } else {
+        const size_t ch_smem = (size_t)kChainRing * kChainRows * 32 * sizeof(float);
+        GSL_CUDA_TRY(cudaFuncSetAttribute(ordered_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch_smem));
+        ordered_chain_kernel<<<grid, kOrdThreads, ch_smem, st>>>(data, D, members, start, total, old_centroids, new_centroids);
+        GSL_LAUNCH_CHECK("ordered_chain_kernel");
+    }
     shift_kernel<<<1, 256, 0, st>>>(new_centroids, old_centroids, K * D, shift, bad_label);
     GSL_LAUNCH_CHECK("shift_kernel");
     return GSL_OK;
