@@ -37,6 +37,9 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // Cached per-device facts (SM count) so launches can size persistent grids.
 int sm_count();
 
+// lift.cu: one high-priority non-blocking helper stream per device, created on first use (NULL if that fails).
+cudaStream_t helper_stream();
+
 // kmeans_ordered.cu: scratch for gsl_kmeans_update_ordered.
 size_t ordered_workspace_bytes(int64_t N, int D, int K);
 

@@ -259,6 +259,16 @@ ordered_chain_kernel(const float *__restrict__ data, int D, const int32_t *__res
 constexpr int kStreamRows = 512;       // rows per stage (64 KB)
 constexpr int kStreamStages = 3;
 
+// The chain of the largest cluster is the critical path (2.2 ms at C5, where one cluster holds 12 % of the
+// rows), the gather in front of it is not: clusters with at least 1/16 of the members are gathered first and
+// their chains start on a helper stream while the caller's stream gathers and sums the rest.
+//   phase 0: every cluster   1: the big ones   2: the others
+__device__ __forceinline__ bool in_phase(int phase, int64_t n, int64_t n_members)
+{
+    const bool big = n * 16 >= n_members && n > 0;
+    return phase == 0 || (phase == 1) == big;
+}
+
 // rows32[chunk][group][lane][4]: the rows of a cluster start at a multiple of four slots (pstart), four
 // consecutive rows form a group, and a lane's four values of a group are contiguous -- the stream kernel
 // fetches them with one 16-byte shared load.  One warp per group: four member rows read lane = dimension,
@@ -266,8 +276,9 @@ constexpr int kStreamStages = 3;
 __global__ void __launch_bounds__(256)
 ordered_gather_kernel(const float *__restrict__ data, int D, int n_chunks, const int32_t *__restrict__ members,
                       const int64_t *__restrict__ start, const int64_t *__restrict__ pstart, const int64_t *__restrict__ total,
-                      int K, int64_t slots_pad, float *__restrict__ rows32)
+                      int K, int64_t slots_pad, float *__restrict__ rows32, int phase)
 {
+    const int64_t n_members = start[K - 1] + total[K - 1];
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -281,6 +292,7 @@ ordered_gather_kernel(const float *__restrict__ data, int D, int n_chunks, const
             else hi = mid - 1;
         }
         const int64_t m = slot - pstart[lo], n = total[lo], s = start[lo] + m;
+        if (!in_phase(phase, n, n_members)) continue;
         int row[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) row[j] = m + j < n ? __ldg(members + s + j) : -1;
@@ -296,14 +308,16 @@ ordered_gather_kernel(const float *__restrict__ data, int D, int n_chunks, const
 }
 
 __global__ void __launch_bounds__(32)
-ordered_stream_kernel(const float *__restrict__ rows32, int64_t slots_pad, int D, const int64_t *__restrict__ pstart,
-                      const int64_t *__restrict__ total, const float *__restrict__ old_c, float *__restrict__ new_c)
+ordered_stream_kernel(const float *__restrict__ rows32, int64_t slots_pad, int D, int K, const int64_t *__restrict__ start,
+                      const int64_t *__restrict__ pstart, const int64_t *__restrict__ total, const float *__restrict__ old_c,
+                      float *__restrict__ new_c, int phase)
 {
     extern __shared__ __align__(128) float sbuf[];           // [kStreamStages][kStreamRows / 4][32][4]
     __shared__ __align__(8) unsigned long long bars[kStreamStages];
     const int k = blockIdx.x, lane = threadIdx.x, d = blockIdx.y * 32 + lane;
     const bool live = d < D;
     const int64_t n = total[k];
+    if (!in_phase(phase, n, start[K - 1] + total[K - 1])) return;
     if (n == 0) {
         if (live) new_c[(size_t)k * D + d] = old_c[(size_t)k * D + d];   // km:126 else-branch
         return;
@@ -456,16 +470,38 @@ extern "C" int gsl_kmeans_update_ordered(const float *data, const int32_t *label
     static const bool streamed = [] { const char *e = getenv("GSLIFT_ORDERED_STREAM"); return !(e && e[0] == '0'); }();
     if (streamed) {
         float *rows32 = reinterpret_cast<float *>(base + L.rows32 - 256);
-        if (N > 0) {
-            const int64_t warps = (N + 3) / 4 + K;
-            const unsigned g = (unsigned)std::min<int64_t>((warps * 32 + 255) / 256, (int64_t)sm_count() * 16);
-            ordered_gather_kernel<<<g, 256, 0, st>>>(data, D, (int)grid.y, members, start, pstart, total, K, (int64_t)L.slots_pad, rows32);
-            GSL_LAUNCH_CHECK("ordered_gather_kernel");
-        }
         const size_t st_smem = (size_t)kStreamStages * kStreamRows * 32 * sizeof(float);
         GSL_CUDA_TRY(cudaFuncSetAttribute(ordered_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st_smem));
-        ordered_stream_kernel<<<grid, 32, st_smem, st>>>(rows32, (int64_t)L.slots_pad, D, pstart, total, old_centroids, new_centroids);
-        GSL_LAUNCH_CHECK("ordered_stream_kernel");
+        const int64_t warps = (N + 3) / 4 + K;
+        const unsigned g = (unsigned)std::min<int64_t>((warps * 32 + 255) / 256, (int64_t)sm_count() * 16);
+        auto gather = [&](int phase, cudaStream_t s) -> int {
+            if (N == 0) return GSL_OK;
+            ordered_gather_kernel<<<g, 256, 0, s>>>(data, D, (int)grid.y, members, start, pstart, total, K, (int64_t)L.slots_pad, rows32, phase);
+            GSL_LAUNCH_CHECK("ordered_gather_kernel");
+            return GSL_OK;
+        };
+        auto chains = [&](int phase, cudaStream_t s) -> int {
+            ordered_stream_kernel<<<grid, 32, st_smem, s>>>(rows32, (int64_t)L.slots_pad, D, K, start, pstart, total, old_centroids, new_centroids, phase);
+            GSL_LAUNCH_CHECK("ordered_stream_kernel");
+            return GSL_OK;
+        };
+        cudaStream_t side = N >= (1 << 18) ? helper_stream() : nullptr;
+        cudaEvent_t ev = nullptr;
+        if (side && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); side = nullptr; }
+        if (!side) {
+            if (int rc = gather(0, st)) return rc;
+            if (int rc = chains(0, st)) return rc;
+        } else {
+            int rc = gather(1, st);
+            if (rc == GSL_OK && (cudaEventRecord(ev, st) != cudaSuccess || cudaStreamWaitEvent(side, ev, 0) != cudaSuccess)) rc = fail(GSL_ECUDA, "gsl_kmeans_update_ordered: fork failed");
+            if (rc == GSL_OK) rc = chains(1, side);
+            if (rc == GSL_OK) rc = gather(2, st);
+            if (rc == GSL_OK) rc = chains(2, st);
+            // the caller's stream continues only after the big clusters' chains (also when something above failed)
+            if (cudaEventRecord(ev, side) != cudaSuccess || cudaStreamWaitEvent(st, ev, 0) != cudaSuccess) { if (rc == GSL_OK) rc = fail(GSL_ECUDA, "gsl_kmeans_update_ordered: join failed"); }
+            cudaEventDestroy(ev);
+            if (rc != GSL_OK) return rc;
+        }
     } else {
         const size_t ch_smem = (size_t)kChainRing * kChainRows * 32 * sizeof(float);
         GSL_CUDA_TRY(cudaFuncSetAttribute(ordered_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch_smem));
