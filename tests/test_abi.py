@@ -57,6 +57,47 @@ def test_argument_validation_needs_no_device():
         native.check(L.gsl_kmeans_finalize(None, None, 4, 3, None, None, None))
 
 
+def test_next_row_entry_points_validate_arguments_without_a_device():
+    """Viewer / region-growing entry points: bad arguments are refused before any
+    CUDA call, workspace queries are host arithmetic."""
+    import numpy as np
+    native = pkg("_native")
+    L = native.lib()
+    vp = np.zeros(16)
+    assert L.gsl_viewer_depth_sort(None, 10, 8, vp.ctypes.data, None, None, 0, None) == -1
+    assert L.gsl_viewer_depth_sort(None, 0, 8, vp.ctypes.data, None, None, 0, None) == 0          # empty cloud: nothing to do
+    assert L.gsl_viewer_depth_sort(None, 10, 2, vp.ctypes.data, None, None, 0, None) == -1        # stride < 3
+    assert L.gsl_viewer_hit_test(None, None, 10, 8, vp.ctypes.data, 0.0, 0.0, 1.0, 1.0, -999999, None, None, None, 0, None) == -1
+    assert L.gsl_viewer_sort_workspace_bytes(1_000_000) >= 3 * 4 * 1_000_000 and L.gsl_viewer_hit_workspace_bytes() > 0
+    assert L.gsl_region_knn_pca(None, 10, 0, None, None, None, None, None, None, None, 0, None) == -1    # k < 1
+    assert L.gsl_region_knn_pca(None, 10, 3, None, None, None, None, None, None, None, 0, None) == -1    # null points
+    assert L.gsl_region_knn_pca(None, 0, 3, None, None, None, None, None, None, None, 0, None) == 0
+    assert L.gsl_region_workspace_bytes(200_000) >= 200_000 * (16 + 16) + 8 ** 7 * 4
+
+
+def test_region_grow_host_helper_equals_oracle(oracle):
+    """gsl_region_grow is host code inside the product library (the growth loop of segmentation_3D, rg:188-215,
+    is serial): same partition as the oracle's restatement and as the reference run verbatim."""
+    import numpy as np
+    from util import GOLDEN
+    L = pkg("_native").lib()
+    for name in ("region_planes_k40", "region_planes_k400", "region_planes_k2000"):
+        g = np.load(os.path.join(GOLDEN, name + ".npz"))
+        knn = np.ascontiguousarray(g["knn_seg"], np.int32)
+        normals = np.ascontiguousarray(g["normals"], np.float64)
+        residuals = np.ascontiguousarray(g["residuals"], np.float64)
+        n, k = knn.shape
+        region_of = np.empty(n, np.int32)
+        sizes = np.empty(n, np.int64)
+        r = L.gsl_region_grow(knn.ctypes.data, k, normals.ctypes.data, residuals.ctypes.data, n, 0.1, 0.05,
+                              region_of.ctypes.data, sizes.ctypes.data)
+        want, n_want = oracle.region_grow(knn, normals, residuals, 0.1, 0.05)
+        assert r == n_want == int(g["n_regions"])
+        assert np.array_equal(region_of, want)                        # both number regions in creation order
+        assert np.array_equal(np.bincount(region_of, minlength=r), sizes[:r])
+        assert len(set(zip(region_of.tolist(), g["region_of"].tolist()))) == r
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():
