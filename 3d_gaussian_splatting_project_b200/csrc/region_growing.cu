@@ -48,6 +48,14 @@ constexpr int kDigits = 1 << kDigitBits;
 constexpr int kWarps = 8;
 constexpr int kMaxRanges = 343;            // (2 * 3 + 1)^3 cells
 constexpr int kMaxList = 64;               // neighbour lists are returned for k <= 64
+constexpr int kBucketCap = 256;            // candidates of the k-th value's histogram bucket resolved in shared memory
+
+struct BucketEntry {                       // 16 bytes: kBucketCap of them reuse the 4 KB of the histogram
+    double d2;
+    uint32_t pos;                          // position in the sorted array
+    uint32_t idx;                          // original index
+};
+static_assert(sizeof(BucketEntry) * kBucketCap <= sizeof(uint32_t) * kDigits, "bucket list aliases the histogram");
 
 struct GridInfo {            // device-resident, written by bbox_final_kernel
     double lo[3];
@@ -261,7 +269,7 @@ __device__ int build_ranges(const Tables &T, int64_t N, int L, int ring, int cx,
     return cnt;
 }
 
-// Calls f(valid, point) for every point of the ranges, all 32 lanes in lockstep and all lanes busy: lane l
+// Calls f(valid, point, position in the sorted array) for every point of the ranges, all 32 lanes in lockstep and all lanes busy: lane l
 // takes candidates l, l + 32, ... of the flat index space and advances its own range cursor.
 template <class F>
 __device__ __forceinline__ void walk(const float4 *__restrict__ sorted, const WarpScratch &sc, uint32_t total, unsigned lane, F f)
@@ -272,6 +280,7 @@ __device__ __forceinline__ void walk(const float4 *__restrict__ sorted, const Wa
     uint32_t r_end = sc.end[0], off = sc.off[0];
     for (uint32_t v0 = 0; v0 < total; v0 += 32 * U) {
         float4 p[U];
+        uint32_t at[U];
         bool valid[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -283,11 +292,12 @@ __device__ __forceinline__ void walk(const float4 *__restrict__ sorted, const Wa
                 r_end = sc.end[r];
                 off = sc.off[r];
             }
-            p[u] = __ldg(sorted + (off + vv));
+            at[u] = off + vv;
+            p[u] = __ldg(sorted + at[u]);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u)
-            if (v0 + 32 * u < total) f(valid[u], p[u]);      // warp-uniform condition
+            if (v0 + 32 * u < total) f(valid[u], p[u], at[u]);      // warp-uniform condition
     }
 }
 
@@ -369,7 +379,7 @@ __global__ void __launch_bounds__(kWarps * 32, 3) knn_pca_kernel(const float4 *_
             const unsigned long long b = (unsigned long long)__double_as_longlong(d2);
             return (b > floor_bits ? b : floor_bits) - floor_bits;
         };
-        unsigned long long n_walks = 0, n_walked = 0;
+        unsigned long long n_walks = 0, n_walked = 0, n_failed = 0, n_select = 0;
 
         // 1. the finest cube that provably holds the k nearest neighbours; the counting walk also fills the
         //    histogram of the leading digit
@@ -388,7 +398,10 @@ __global__ void __launch_bounds__(kWarps * 32, 3) knn_pca_kernel(const float4 *_
                     found = true;
                     break;
                 }
-                if (in_cube < k) continue;
+                // a ball of `ring` cells fills 0.155 / 0.27 / 0.33 of its cube: do not walk a cube whose points would
+                // have to be 25 % denser inside the ball than outside to reach k (a walk that fails is wasted)
+                const double fill = ring == 1 ? 0.155 : (ring == 2 ? 0.268 : 0.329);
+                if ((double)in_cube * fill * 1.25 < (double)k) continue;
                 // every point outside the cube is farther than ring cells of this level
                 const double rad = (double)ring * G.h7 * (double)(1 << (kLevels - L)) * (1.0 - 1e-9);
                 R2 = rad * rad;
@@ -399,7 +412,7 @@ __global__ void __launch_bounds__(kWarps * 32, 3) knn_pca_kernel(const float4 *_
                 for (int d = lane; d < kDigits; d += 32) sc.hist[d] = 0;
                 __syncwarp();
                 int inside = 0;
-                walk(sorted, sc, (uint32_t)in_cube, lane, [&](bool valid, const float4 p) {
+                walk(sorted, sc, (uint32_t)in_cube, lane, [&](bool valid, const float4 p, uint32_t) {
                     const double d2 = sqdist(p, qx, qy, qz);
                     if (valid && d2 <= R2) {
                         ++inside;
@@ -416,6 +429,7 @@ __global__ void __launch_bounds__(kWarps * 32, 3) knn_pca_kernel(const float4 *_
                     found = true;
                     break;
                 }
+                ++n_failed;
             }
             if (found) break;
         }
@@ -424,6 +438,7 @@ __global__ void __launch_bounds__(kWarps * 32, 3) knn_pca_kernel(const float4 *_
         unsigned long long prefix = 0;      // the digits chosen so far = key >> shift
         int shift = top_shift + kDigitBits, need = k;
         bool exact = false;                 // every key with (key >> shift) <= prefix is selected
+        bool use_list = false;              // the bucket of the k-th value is small: resolved from a list in shared memory
         bool first = true;
         while (shift > 0 && !exact) {
             const int bits = shift >= kDigitBits ? kDigitBits : shift;
@@ -431,13 +446,14 @@ __global__ void __launch_bounds__(kWarps * 32, 3) knn_pca_kernel(const float4 *_
             if (!(first && have_hist)) {
                 for (int d = lane; d < kDigits; d += 32) sc.hist[d] = 0;
                 __syncwarp();
-                walk(sorted, sc, (uint32_t)in_cube, lane, [&](bool valid, const float4 p) {
+                walk(sorted, sc, (uint32_t)in_cube, lane, [&](bool valid, const float4 p, uint32_t) {
                     const double d2 = sqdist(p, qx, qy, qz);
                     const unsigned long long key = key_of(d2);
                     if (valid && d2 <= R2 && (first || (key >> shift) == prefix))
                         atomicAdd(&sc.hist[(unsigned)(key >> new_shift) & ((1u << bits) - 1u)], 1u);
                 });
                 ++n_walks;
+                ++n_select;
                 n_walked += (unsigned long long)in_cube;
                 __syncwarp();
             }
@@ -484,6 +500,10 @@ __global__ void __launch_bounds__(kWarps * 32, 3) knn_pca_kernel(const float4 *_
             shift = new_shift;
             exact = need == bucket;
             first = false;
+            if (!exact && bucket <= kBucketCap) {
+                use_list = true;            // the next walk collects the bucket and sums everything below it
+                break;
+            }
         }
         // here: keys with (key >> shift) < prefix are all selected; of those equal to prefix, `need` are
         // (all of them when `exact`; otherwise shift == 0 and they are exact ties: lowest indices win)
@@ -511,21 +531,57 @@ __global__ void __launch_bounds__(kWarps * 32, 3) knn_pca_kernel(const float4 *_
                 n_list += __popc(m);
             }
         };
-        walk(sorted, sc, (uint32_t)in_cube, lane, [&](bool valid, const float4 p) {
+        BucketEntry *blist = reinterpret_cast<BucketEntry *>(sc.hist);        // the histogram is not needed any more
+        int n_bucket = 0;
+        __syncwarp();
+        walk(sorted, sc, (uint32_t)in_cube, lane, [&](bool valid, const float4 p, uint32_t at) {
             const double d2 = sqdist(p, qx, qy, qz);
             const unsigned long long key = key_of(d2) >> shift;
-            const bool sel = valid && d2 <= R2 && (exact ? key <= prefix : key < prefix);
+            const bool in_ball = valid && d2 <= R2;
+            const bool sel = in_ball && (exact ? key <= prefix : key < prefix);
             take(sel, p, d2);
+            if (use_list) {
+                const bool mine = in_ball && key == prefix;
+                const unsigned m = __ballot_sync(0xffffffffu, mine);
+                if (mine) {
+                    const int slot = n_bucket + __popc(m & radix::lanemask_lt());
+                    if (slot < kBucketCap) blist[slot] = BucketEntry{d2, at, __float_as_uint(p.w)};
+                }
+                n_bucket += __popc(m);
+            }
         });
         ++n_walks;
         n_walked += (unsigned long long)in_cube;
-        if (!exact) {
-            // exact ties at the k-th distance: take the `need` lowest original indices among them
+        if (use_list) {
+            // the `need` smallest of the bucket by (distance, index): rank by counting, 32 entries at a time
+            __syncwarp();
+            const int nb = min(n_bucket, kBucketCap);
+            for (int a0 = 0; a0 < nb; a0 += 32) {
+                const int a = a0 + (int)lane;
+                bool sel = false;
+                float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+                double d2 = 0.0;
+                if (a < nb) {
+                    const BucketEntry e = blist[a];
+                    int rank = 0;
+                    for (int b = 0; b < nb; ++b) {
+                        const BucketEntry o = blist[b];
+                        rank += (o.d2 < e.d2 || (o.d2 == e.d2 && o.idx < e.idx)) ? 1 : 0;
+                    }
+                    sel = rank < need;
+                    d2 = e.d2;
+                    if (sel) p = __ldg(sorted + e.pos);
+                }
+                take(sel, p, d2);
+            }
+        }
+        if (!exact && !use_list) {
+            // exact ties at the k-th distance (a bucket too large for the list that stayed tied through every digit): take the `need` lowest original indices among them
             long long last = -1;
             for (int t = 0; t < need; ++t) {
                 unsigned long long best = ~0ull;      // (index << 32) | sorted position is not needed: index is unique
                 float4 bp = make_float4(0.f, 0.f, 0.f, 0.f);
-                walk(sorted, sc, (uint32_t)in_cube, lane, [&](bool valid, const float4 p) {
+                walk(sorted, sc, (uint32_t)in_cube, lane, [&](bool valid, const float4 p, uint32_t) {
                     const double d2 = sqdist(p, qx, qy, qz);
                     const unsigned long long key = key_of(d2);
                     const long long idx = (long long)__float_as_uint(p.w);
@@ -592,6 +648,8 @@ __global__ void __launch_bounds__(kWarps * 32, 3) knn_pca_kernel(const float4 *_
         if (stats && lane == 0) {
             atomicAdd(&stats[0], n_walks);
             atomicAdd(&stats[1], n_walked);
+            atomicAdd(&stats[2], n_failed);
+            atomicAdd(&stats[3], n_select);
         }
     }
 }

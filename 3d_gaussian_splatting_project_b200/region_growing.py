@@ -61,8 +61,8 @@ def knn_pca(V1, k: int, normals_in=None, want_normals=True, want_residuals=True,
         out["centroids"] = torch.empty((N, 3), dtype=torch.float64, device=dev)
     if want_knn:
         out["knn"] = torch.empty((N, int(k)), dtype=torch.int32, device=dev)
-    if want_stats:          # [walks over candidate cells, points visited]: work counters
-        out["stats"] = torch.zeros(2, dtype=torch.int64, device=dev)
+    if want_stats:          # [walks over candidate cells, points visited, cubes too small, further select walks]
+        out["stats"] = torch.zeros(4, dtype=torch.int64, device=dev)
     L = lib()
     ws = ops._ws.get(dev, L.gsl_region_workspace_bytes(N))
     ptr = lambda name: out[name].data_ptr() if name in out else None

@@ -337,8 +337,9 @@ int gsl_viewer_hit_test(const float *pos, const int32_t *labels, int64_t N, int 
  *   normals     optional float64 [N][3] out        residuals  optional float64 [N] out
  *   centroids   optional float64 [N][3] out        knn        optional int32 [N][k] out, k <= 64:
  *               neighbour indices in increasing (distance, index) order (KDTree.query order)
- *   stats       optional uint64 [2], device, caller zeroes: += walks over candidate cells, += points
- *               visited by those walks (work counters for benchmarks)
+ *   stats       optional uint64 [4], device, caller zeroes: += walks over candidate cells, += points visited by
+ *               those walks, += cubes that turned out too small, += walks spent on further select digits
+ *               (work counters for benchmarks)
  */
 size_t gsl_region_workspace_bytes(int64_t N);
 int gsl_region_knn_pca(const float *pos, int64_t N, int k, const double *normals_in, double *normals,

@@ -154,7 +154,8 @@ def test_c1_size_cloud_k2000_sample_against_oracle(oracle):
     torch.cuda.synchronize()
     st = rg.knn_pca(dpos, 2000, want_stats=True)["stats"].cpu().numpy()
     print(f"\n200 000 points, k = 2000: {ev0.elapsed_time(ev1):.1f} ms on the GPU, {st[0] / 2e5:.2f} walks per query, "
-          f"{st[1] / 4e8:.2f} points visited per neighbour found")
+          f"{st[1] / 4e8:.2f} points visited per neighbour found, {st[2] / 2e5:.2f} cubes too small, "
+          f"{st[3] / 2e5:.2f} further select walks per query")
     assert st[0] / 2e5 < 8
     q0, q1 = 100_000, 100_600
     ref = oracle.region_knn_pca(pos, 2000, queries=(q0, q1))
