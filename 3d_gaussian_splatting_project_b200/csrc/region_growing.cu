@@ -57,11 +57,14 @@ struct BucketEntry {                       // 16 bytes: kBucketCap of them reuse
 };
 static_assert(sizeof(BucketEntry) * kBucketCap <= sizeof(uint32_t) * kDigits, "bucket list aliases the histogram");
 
-struct GridInfo {            // device-resident, written by bbox_final_kernel
-    double lo[3];
+struct GridInfo {            // device-resident, written by bbox_final_kernel, refined by grid_box_kernel
+    double lo[3];            // low corner of the grid
     double h7;               // side of a finest cell
     double inv_h7;
+    double full_lo[3], full_hi[3];     // bounding box of the points
 };
+
+constexpr int kBoxBins = 1024;          // coordinate histogram bins per axis
 
 struct Tables {
     const uint32_t *start[kLevels + 1];    // [L] : 8^L + 1 entries, L = 1..7
@@ -152,7 +155,73 @@ __global__ void __launch_bounds__(256) bbox_final_kernel(const float *__restrict
     for (int a = 0; a < 3; ++a) side = fmax(side, (double)hi[a] - (double)lo[a]);
     if (!(side > 0)) side = 1.0;                       // all points coincide
     side *= 1.0 + 1e-6;
-    for (int a = 0; a < 3; ++a) g->lo[a] = (double)lo[a];
+    for (int a = 0; a < 3; ++a) {
+        g->lo[a] = (double)lo[a];
+        g->full_lo[a] = (double)lo[a];
+        g->full_hi[a] = (double)hi[a];
+    }
+    g->h7 = side / kFinest;
+    g->inv_h7 = kFinest / side;
+}
+
+// The grid should resolve where the points ARE: a few far outliers (floaters are common in splat
+// clouds) would otherwise stretch the 128^3 cells until the whole scene sits in a handful of them and
+// every query walks nearly everything.  So the grid covers, per axis, the 0.5 % .. 99.5 % quantile
+// range (from a 1024-bin histogram over the bounding box) and points outside it are assigned to the
+// border cells.  That keeps the search exact: clamping a coordinate into the grid's box is
+// order preserving and non-expansive, so two points whose cells differ by more than `ring` along an
+// axis are at least ring * cell_size apart along that axis, clamped or not.
+__global__ void __launch_bounds__(256) coord_hist_kernel(const float *__restrict__ pos, int64_t N, const GridInfo *__restrict__ g,
+                                                         unsigned *__restrict__ hist)
+{
+    __shared__ unsigned sh[3][kBoxBins];
+    for (int i = threadIdx.x; i < 3 * kBoxBins; i += 256) (&sh[0][0])[i] = 0u;
+    __syncthreads();
+    double lo[3], scale[3];
+    for (int a = 0; a < 3; ++a) {
+        lo[a] = g->full_lo[a];
+        const double ext = g->full_hi[a] - lo[a];
+        scale[a] = ext > 0 ? kBoxBins / ext : 0.0;
+    }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const int b = min(kBoxBins - 1, max(0, (int)(((double)pos[3 * i + a] - lo[a]) * scale[a])));
+            atomicAdd(&sh[a][b], 1u);
+        }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * kBoxBins; i += 256) {
+        const unsigned c = (&sh[0][0])[i];
+        if (c) atomicAdd(&hist[i], c);
+    }
+}
+
+__global__ void grid_box_kernel(const unsigned *__restrict__ hist, int64_t N, GridInfo *__restrict__ g)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const unsigned long long cut = (unsigned long long)(N / 200);           // 0.5 % of the points on either side
+    double lo[3], hi[3], side = 0;
+    for (int a = 0; a < 3; ++a) {
+        const double ext = g->full_hi[a] - g->full_lo[a], w = ext / kBoxBins;
+        unsigned long long run = 0;
+        int b0 = 0, b1 = kBoxBins - 1;
+        for (int b = 0; b < kBoxBins; ++b) {
+            run += hist[a * kBoxBins + b];
+            if (run > cut) { b0 = b; break; }
+        }
+        run = 0;
+        for (int b = kBoxBins - 1; b >= 0; --b) {
+            run += hist[a * kBoxBins + b];
+            if (run > cut) { b1 = b; break; }
+        }
+        if (b1 < b0) b1 = b0;
+        lo[a] = g->full_lo[a] + b0 * w;                                       // left edge of the first kept bin
+        hi[a] = g->full_lo[a] + (b1 + 1) * w;                                 // right edge of the last one
+        side = fmax(side, hi[a] - lo[a]);
+    }
+    if (!(side > 0)) side = 1.0;
+    side *= 1.0 + 1e-6;
+    for (int a = 0; a < 3; ++a) g->lo[a] = lo[a];
     g->h7 = side / kFinest;
     g->inv_h7 = kFinest / side;
 }
@@ -655,7 +724,7 @@ __global__ void __launch_bounds__(kWarps * 32, 3) knn_pca_kernel(const float4 *_
 }
 
 struct Plan {
-    size_t keys_a, keys_b, idx_a, idx_b, hist, sorted, tables[kLevels + 1], ginfo, bbox, total;
+    size_t keys_a, keys_b, idx_a, idx_b, hist, sorted, tables[kLevels + 1], ginfo, bbox, chist, total;
 };
 static Plan plan(int64_t N)
 {
@@ -675,6 +744,7 @@ static Plan plan(int64_t N)
     }
     p.ginfo = o; o = align_up(o + sizeof(GridInfo), 256);
     p.bbox = o;  o = align_up(o + 1024 * 6 * sizeof(float), 256);
+    p.chist = o; o = align_up(o + 3 * kBoxBins * sizeof(unsigned), 256);
     p.total = o;
     return p;
 }
@@ -710,6 +780,12 @@ extern "C" int gsl_region_knn_pca(const float *pos, int64_t N, int k, const doub
     GSL_LAUNCH_CHECK("rg::bbox_kernel");
     rg::bbox_final_kernel<<<1, 256, 0, st>>>(bbox, grid, ginfo);
     GSL_LAUNCH_CHECK("rg::bbox_final_kernel");
+    unsigned *chist = (unsigned *)(w + p.chist);
+    GSL_CUDA_TRY(cudaMemsetAsync(chist, 0, 3 * rg::kBoxBins * sizeof(unsigned), st));
+    rg::coord_hist_kernel<<<std::min(grid, sm_count() * 4), 256, 0, st>>>(pos, N, ginfo, chist);
+    GSL_LAUNCH_CHECK("rg::coord_hist_kernel");
+    rg::grid_box_kernel<<<1, 32, 0, st>>>(chist, N, ginfo);
+    GSL_LAUNCH_CHECK("rg::grid_box_kernel");
     const int wide = (int)std::min<int64_t>((N + 255) / 256, (int64_t)sm_count() * 8);
     rg::cell_key_kernel<<<wide, 256, 0, st>>>(pos, N, ginfo, keys_a);
     GSL_LAUNCH_CHECK("rg::cell_key_kernel");

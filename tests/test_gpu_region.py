@@ -160,3 +160,32 @@ def test_c1_size_cloud_k2000_sample_against_oracle(oracle):
     q0, q1 = 100_000, 100_600
     ref = oracle.region_knn_pca(pos, 2000, queries=(q0, q1))
     check_against(oracle, pos, 2000, got["normals"].cpu().numpy(), got["residuals"].cpu().numpy(), ref, rows=(q0, q1))
+
+
+def test_floaters_do_not_degrade_the_grid(oracle):
+    """Far outliers (floaters) stretch the bounding box a thousandfold; the grid is laid over the 0.5 - 99.5 %
+    quantile range instead, so the search stays local -- and exact, outliers included."""
+    rg = pkg("region_growing")
+    rng = np.random.default_rng(8)
+    pos = _blobs(rng, 100_000)
+    far = rng.uniform(-3000, 3000, size=(150, 3)).astype(np.float32)
+    pos = np.concatenate((pos, far))[rng.permutation(100_150)]
+    dpos = torch.from_numpy(pos).cuda()
+    rg.knn_pca(dpos, 64, want_knn=True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    got = rg.knn_pca(dpos, 64, want_knn=True, want_stats=True)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    visited = float(got["stats"][1]) / (len(pos) * 64)
+    print(f"\n100 150 points with 150 floaters, k = 64: {ms:.1f} ms, {visited:.1f} points visited per neighbour found")
+    assert visited < 200                                  # the whole cloud in one cell would be ~3000
+    far_rows = np.flatnonzero(np.abs(pos).max(1) > 100)[:40]
+    knn = got["knn"].cpu().numpy()
+    for q0 in (0, 50_000):                                # two slices of ordinary points ...
+        ref = oracle.region_knn_pca(pos, 64, want_knn=True, queries=(q0, q0 + 300))
+        assert np.array_equal(knn[q0:q0 + 300], ref["knn"][q0:q0 + 300])
+    for r in far_rows:                                    # ... and the floaters themselves
+        ref = oracle.region_knn_pca(pos, 64, want_knn=True, queries=(int(r), int(r) + 1))
+        assert np.array_equal(knn[r], ref["knn"][r])
