@@ -27,6 +27,8 @@
 // is launch-bound, so the small kernels of round 1 (grid, tile boxes, planes) were folded away.
 // The order inside a cell follows the input order (the sort is stable), so the whole ordering is
 // deterministic.  (A 1024^3 grid with 30-bit keys was measured: one more sort pass, same gather time.)
+#include <algorithm>
+
 #include "common.cuh"
 #include "lift_internal.cuh"
 
@@ -276,26 +278,36 @@ __device__ __forceinline__ bool box_may_be_visible(const float4 *__restrict__ pl
 // every factor rounded up; 1/2 - E, rounded down to a multiple of 2^-16, is what a pair's offset
 // from the pixel centre is compared with; bit 0 of the verdict says the tile is `interior`
 // (box_may_be_visible), which lets the sweep skip the clamp of the ring coordinates.
-__global__ void __launch_bounds__(256)
+// A thread owns a VIEW (its five planes and facts stay in registers) and walks tiles; the eight floats of
+// a tile's box are two broadcast loads.  (One thread per (tile, view), each re-reading the view's ~150
+// bytes of tables, took 75 us at 6 M x 300 -- bound by L1 traffic.)
+__global__ void __launch_bounds__(1024)
 order_verdict_kernel(const float *__restrict__ box, int64_t n_tiles, const float4 *__restrict__ planes,
                      const ViewFacts *__restrict__ facts, int V, int v_pad, int cull, int exact_only,
                      uint16_t *__restrict__ verdict)
 {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t tile = idx / v_pad;
-    const int v = (int)(idx - tile * v_pad);
-    if (tile >= n_tiles) return;
+    const int v = blockIdx.y * blockDim.x + threadIdx.x;
+    if (v >= v_pad) return;
+    const bool real = v < V;
+    ViewFacts f = {};
+    float4 pl[5] = {};
+    if (real) {
+        f = facts[v];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) pl[j] = planes[(size_t)v * 5 + j];
+    }
+    const unsigned slow = ((f.flags & kViewScreen) && !exact_only) ? kVerdictGeneral : kVerdictF64;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     unsigned out = kVerdictCull;
-    if (v < V) {
-        const float *b = box + tile * 8;
-        const ViewFacts f = facts[v];
-        const unsigned slow = ((f.flags & kViewScreen) && !exact_only) ? kVerdictGeneral : kVerdictF64;
+    if (real) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4 *>(box + tile * 8)), b1 = __ldg(reinterpret_cast<const float4 *>(box + tile * 8) + 1);
+        const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
         out = slow;
         if (b[6] == 0.f) {                                                  // a non-finite member: never cull, never fast
             const float lo[3] = {b[0], b[1], b[2]}, hi[3] = {b[3], b[4], b[5]};
             float cz_lo;
             bool interior;
-            const bool vis = box_may_be_visible(planes + (size_t)v * 5, lo, hi, cz_lo, interior);
+            const bool vis = box_may_be_visible(pl, lo, hi, cz_lo, interior);
             if (!vis && cull) {
                 out = kVerdictCull;
             } else if (slow == kVerdictGeneral && (f.flags & kViewBorder) && cz_lo > 0.f) {
@@ -313,6 +325,7 @@ order_verdict_kernel(const float *__restrict__ box, int64_t n_tiles, const float
         }
     }
     verdict[tile * v_pad + v] = (uint16_t)out;
+    }
 }
 
 OrderWs order_layout(int64_t N, int V)
@@ -377,8 +390,9 @@ int order_gaussians(const float *pos, int64_t N, int V, bool sort, bool exact_on
     }
     order_permute_kernel<<<rows_grid, 256, 0, st>>>(pos, N, perm, pos_sorted, tilebox);       // rows_grid == n_tiles
     GSL_LAUNCH_CHECK("order_permute_kernel");
-    const int64_t threads = n_tiles * (int64_t)v_pad;
-    order_verdict_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(tilebox, n_tiles, planes, d_facts, V, v_pad, sort ? 1 : 0, exact_only ? 1 : 0, verdict);
+    const int vthreads = v_pad < 1024 ? (v_pad + 31) / 32 * 32 : 1024;                          // a thread per view
+    const dim3 vgrid((unsigned)std::min<int64_t>(n_tiles, (int64_t)sm_count() * (2048 / vthreads) * 2), (unsigned)((v_pad + vthreads - 1) / vthreads));
+    order_verdict_kernel<<<vgrid, vthreads, 0, st>>>(tilebox, n_tiles, planes, d_facts, V, v_pad, sort ? 1 : 0, exact_only ? 1 : 0, verdict);
     GSL_LAUNCH_CHECK("order_verdict_kernel");
     return GSL_OK;
 }
